@@ -1,0 +1,171 @@
+/* pf_b200.h — C ABI of libpf_b200.so: the B200 (sm_100a) kernels behind PatchFusion's per-tile inference hot path.
+ *
+ * Boundary: the reference is pure Python/PyTorch and has no FFI; the drop-in class
+ * `estimator.models.patchfusion.PatchFusion` (reference `estimator/models/patchfusion.py:55-453`) keeps its Python
+ * surface and its methods call the entry points below through ctypes (patchfusion_b200/lib.py; the stub a reference
+ * maintainer would add is shown in INTEGRATION.md).  Conventions:
+ *   - plain pointers and ints only; every pointer is a DEVICE pointer unless the name ends in _host;
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued asynchronously on it (CUDA-graph capturable);
+ *   - no allocation, no synchronisation, no global mutable state besides one-time kernel attribute setup and a
+ *     tensor-map cache keyed by (pointer, shape);
+ *   - return 0 on success, non-zero on error with a message in pf_last_error() (thread-local);
+ *   - activations are bf16, channels-last (NHWC, row stride `ld` elements); the ViT residual stream, LayerNorm
+ *     statistics, softmax, the metric-bins tail and the stitch canvases are fp32.
+ * Each entry point cites the reference code it replaces (paths relative to the reference repo root).
+ */
+#ifndef PF_B200_H_
+#define PF_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PF_ACT_NONE 0
+#define PF_ACT_RELU 1
+#define PF_ACT_GELU 2      /* exact erf GELU (nn.GELU default) */
+#define PF_ACT_SOFTPLUS 3  /* beta 1, threshold 20 */
+
+/* ---- library ------------------------------------------------------------------------------------------------ */
+const char* pf_last_error(void);
+int pf_version(void);
+/* number of kernels launched by this library since process start (bench.py's gpu_launches) */
+long long pf_launch_count(void);
+
+/* ---- dense contractions: one tcgen05/TMEM/TMA implicit-GEMM kernel ---------------------------------------------
+ * Replaces every nn.Linear / nn.Conv2d(1x1, 3x3 s1 p1) / nn.ConvTranspose2d(k==s) on the path:
+ *   external/torchhub/facebookresearch_dinov2_main/dinov2/layers/attention.py:51,60  mlp.py:36-39
+ *   external/depth_anything/dpt.py:30-60,87-95  blocks.py:53-58,123  estimator/models/patchfusion.py:122-127,263-267
+ *   estimator/models/blocks/guided_fusion_model.py:41-47,59-66  swin_layers.py:45-48,140,162
+ *   external/zoedepth/models/layers/{localbins_layers.py:84-89,110-114, attractor.py:157-162, dist_layers.py:91-98}
+ */
+typedef struct pf_gemm_desc {
+  /* A operand: up to 3 channel-concatenated sources (torch.cat(dim=1) is never materialised) */
+  int32_t num_src;        /* 1..3 */
+  int32_t a_mode;         /* 0: rows x K matrix; 1: NHWC image, 3x3 or 1x1 window */
+  int32_t taps;           /* 1 or 9 (3x3, stride 1, zero pad 1) */
+  int32_t chunks[3];      /* ceil(C_src / 64) */
+  const void* a_ptr[3];   /* bf16 */
+  int32_t a_c[3];         /* channels (columns) of each source, multiple of 8 */
+  int32_t a_ld[3];        /* row (pixel) stride in elements, multiple of 8 */
+  /* M geometry */
+  int32_t M;              /* a_mode 0: rows */
+  int32_t NB, H, W;       /* a_mode 1: batch and image size; also the input grid for pixel-shuffle (ps > 1) */
+  int32_t bh, bw;         /* a_mode 1: pixel tile, bh*bw == 128 (0 = choose) */
+  int32_t tiles_y, tiles_x, m_tiles;   /* filled by the library */
+  /* B operand: packed weights [N_pad, Ktot] bf16 K-major from pf_pack_weight */
+  const void* w_ptr;
+  int32_t N, Ktot;
+  int32_t block_n, n_tiles;            /* block_n: 0 = choose; multiple of 32, <= 256 */
+  /* epilogue: v = act(acc + bias); v += res1 + res2; then one of {bf16 store, f32 store, x += gamma*v} */
+  const float* bias;
+  int32_t act;
+  const void* res1; const void* res2; int32_t res_ld;   /* bf16, same row mapping as out */
+  const float* gamma;                                    /* LayerScale: out (fp32) += gamma * v */
+  void* out; int32_t out_f32; int32_t out_ld; int32_t out_col0;
+  void* out2; int32_t out2_ld;                           /* optional second bf16 output = relu(v) */
+  int32_t ps, ps_cout;                                   /* ConvTranspose k==s as GEMM + pixel shuffle (ps = k) */
+  void* vt; int32_t vt_col0, vt_seq, vt_seq_pad, vt_dim; /* attention V columns written transposed */
+} pf_gemm_desc;
+
+int pf_gemm(pf_gemm_desc* desc, void* stream);
+
+/* Repack an fp32 PyTorch weight into the K-major bf16 panel pf_gemm consumes.
+ *   w: [N, C_total, kh, kw] (Conv2d) or [N, C_total] (Linear, kh=kw=1); `src_c[i]` = channels of concat source i.
+ *   dst: [N_pad, Ktot] bf16, Ktot = sum_i taps * 64*ceil(src_c[i]/64); rows >= N and pad channels are zero.
+ *   scale (nullable, [N]): per-output-channel factor folded into the weights (eval-mode BatchNorm). */
+int pf_pack_weight(const float* w, int32_t N, int32_t N_pad, int32_t num_src, const int32_t* src_c, int32_t taps,
+                   const float* scale, void* dst, void* stream);
+/* ConvTranspose2d(k==s) weight [Cin, Cout, k, k] -> [k*k*Cout, Cin_pad] bf16, row = (ky*k + kx)*Cout + co. */
+int pf_pack_weight_convT(const float* w, int32_t Cin, int32_t Cout, int32_t k, void* dst, void* stream);
+
+/* ---- ViT pieces --------------------------------------------------------------------------------------------- */
+/* LayerNorm over the last dim, fp32 in -> bf16 out (dinov2/layers/block.py:84,87; vision_transformer.py:311;
+ * swin_layers.py:222,265,428).  rows x C; x_ld/out_ld in elements. */
+int pf_layernorm(const float* x, int32_t x_ld, const float* w, const float* b, float eps, int32_t rows, int32_t C,
+                 void* out, int32_t out_ld, void* stream);
+/* Fused softmax(QK^T * scale) V for the DINOv2 blocks (dinov2/layers/attention.py:49-62): qk is the [B*seq, 2*D]
+ * bf16 Q|K part of the qkv GEMM output (row stride qk_ld), vt the transposed V written by pf_gemm;
+ * out [B*seq, D] bf16.  head_dim == 64. */
+int pf_attention(const void* qk, int32_t qk_ld, const void* vt, int32_t B, int32_t seq, int32_t seq_pad,
+                 int32_t heads, float scale, void* out, int32_t out_ld, void* stream);
+/* Normalise (ImageNet mean/std, depth_anything.py:184-190) + 14x14 patch gather (patch_embed.py:76-78) of
+ * B planar fp32 RGB images [B,3,H,W] in [0,1] -> bf16 [B*(H/14)*(W/14), ld] (cols = c*196 + py*14 + px). */
+int pf_patch_im2col(const float* img, int32_t B, int32_t H, int32_t W, void* out, int32_t ld, void* stream);
+/* tokens[b, 0] = cls + pos[0]; tokens[b, 1+i] = patch[b, i] + pos[1+i]  (vision_transformer.py:216-217); fp32 */
+int pf_assemble_tokens(const float* patch, const float* cls, const float* pos, int32_t B, int32_t n_patch, int32_t D,
+                       float* tokens, void* stream);
+
+/* ---- HBM-bound image ops (NHWC bf16 unless noted) ------------------------------------------------------------- */
+/* F.interpolate(mode='bilinear', align_corners=True) (blocks.py:147-149, dpt.py:127,154, guided_fusion_model.py:98,
+ * 192-193, attractor.py:175-183).  Writes into out[..., out_col0:out_col0+C] of a buffer with row stride out_ld. */
+int pf_resize_bilinear(const void* in, int32_t B, int32_t H, int32_t W, int32_t C, int32_t in_ld, int32_t OH,
+                       int32_t OW, void* out, int32_t out_ld, int32_t out_col0, void* stream);
+int pf_resize_bilinear_f32(const float* in, int32_t B, int32_t H, int32_t W, int32_t C, int32_t OH, int32_t OW,
+                           float* out, void* stream);
+/* torchvision.ops.roi_align(feat.repeat(T), boxes, (h,w), h/Hp, aligned=True) with one tap per bin
+ * (patchfusion.py:240-257, guided_fusion_model.py:202).  feat: batch-1 map [h,w,ld]; boxes: T x 4 fp32
+ * (x1,y1,x2,y2, patch_process units) on the device; out [T,h,w,out_ld] at channel offset out_col0.
+ * in_f32 != 0 reads an fp32 map (the coarse depth). */
+int pf_roi_crop_zoom(const void* feat, int32_t in_f32, int32_t h, int32_t w, int32_t C, int32_t in_ld,
+                     const float* boxes, int32_t T, float spatial_scale, void* out, int32_t out_ld,
+                     int32_t out_col0, void* stream);
+/* nn.MaxPool2d(2) (guided_fusion_model.py:78) */
+int pf_maxpool2(const void* in, int32_t B, int32_t H, int32_t W, int32_t C, int32_t in_ld, void* out,
+                int32_t out_ld, void* stream);
+/* stride-2 3x3 pad-1 window gather for dpt.py:54-59 (resize_layers[3]): out [B*OH*OW, 9*C] */
+int pf_im2col_3x3_s2(const void* in, int32_t B, int32_t H, int32_t W, int32_t C, int32_t in_ld, void* out,
+                     void* stream);
+/* Crop T tiles from the planar fp32 image [3,H,W] and resize each to (ph,pw) with bilinear align_corners=True
+ * (baseline_pretrain.py:258-264, depth_anything/transform.py:127-129): origins int32 (y,x) pairs on the device.
+ * out_planar [T,3,ph,pw] fp32 (the tensor the reference hands to fine_forward). */
+int pf_crop_resize(const float* img, int32_t H, int32_t W, const int32_t* origins, int32_t T, int32_t th, int32_t tw,
+                   int32_t ph, int32_t pw, float* out_planar, void* stream);
+/* U-Net input cat[coarse_depth_roi, fine_depth, rgb] (patchfusion.py:269) as NHWC bf16 with `ld` channels */
+int pf_pack_unet_input(const float* coarse_depth_roi, const float* fine_depth, const float* rgb_planar, int32_t T,
+                       int32_t H, int32_t W, void* out, int32_t ld, void* stream);
+/* tokens [B, n, D] bf16 rows -> skip cls handled by caller; generic strided row copy / convert helpers */
+int pf_f32_to_bf16(const float* in, int64_t n, void* out, void* stream);
+
+/* ---- Swin / G2L (estimator/models/blocks/swin_layers.py) ------------------------------------------------------ */
+/* x[h*w, C] fp32 = NHWC bf16 feature + absolute_pos_embed (swin_layers.py:419-422) */
+int pf_g2l_embed(const void* feat, int32_t feat_ld, const float* ape, int32_t n, int32_t C, float* x, void* stream);
+/* LayerNorm(eps) of x[H*W, C] written into the zero-padded (Hp x Wp) token grid, bf16 (swin_layers.py:222-230) */
+int pf_swin_norm_pad(const float* x, const float* w, const float* b, float eps, int32_t H, int32_t W, int32_t Hp,
+                     int32_t Wp, int32_t C, void* out, void* stream);
+/* Window attention on the padded grid with cyclic shift, relative-position bias and the -100 shift mask
+ * (swin_layers.py:133-164, 232-258, 327-345).  qkv [Hp*Wp, 3C] bf16; bias_table [529, heads] fp32;
+ * out [Hp*Wp, C] bf16 in un-shifted token order. */
+int pf_window_attention(const void* qkv, const float* bias_table, int32_t Hp, int32_t Wp, int32_t C, int32_t heads,
+                        int32_t shift, void* out, void* stream);
+/* x[H*W, C] += y[(padded grid), C] cropped (swin_layers.py:260-264); y fp32 */
+int pf_swin_residual_crop(float* x, const float* y, int32_t H, int32_t W, int32_t Wp, int32_t C, void* stream);
+
+/* ---- metric-bins tail (zoedepth_v1.py:173-219, attractor.py:164-208, dist_layers.py:36-121) -------------------- */
+/* x = emb + up(prev_emb) (attractor.py:175-178), NHWC bf16 */
+int pf_add_upsampled(const void* a, int32_t B, int32_t H, int32_t W, int32_t C, const void* prev, int32_t PH,
+                     int32_t PW, void* out, void* stream);
+/* b_new = up(b_prev) + mean_a inv_attractor(A_a - up(b_prev)), alpha=300, gamma=2; fp32 [B,H,W,nbins] */
+int pf_attractor(const float* A, int32_t nA, const float* b_prev, int32_t PH, int32_t PW, int32_t B, int32_t H,
+                 int32_t W, int32_t nbins, int32_t kind_mean, float* b_out, void* stream);
+/* depth = sum_k softmax_k(logbinom(p)/t) * up(b_centers)_k from the 4-channel softplus'd pt map */
+int pf_logbinom_depth(const float* pt, const float* b_centers, int32_t BH, int32_t BW, int32_t B, int32_t H, int32_t W,
+                      int32_t nbins, float min_temp, float max_temp, float* depth, void* stream);
+
+/* ---- stitch (baseline_pretrain.py:310-326, estimator/models/utils.py:21-36 in closed form) --------------------- */
+/* num[y0+i, x0+j] += mask[i,j]*d[t,i,j]; den += mask  — touches only the tile footprints; tiles of one call may
+ * overlap (atomics).  origins: T (y,x) int32 pairs on the device.  up_h/up_w > 0: tiles are nearest-upsampled to
+ * (up_h, up_w) first (random_tile, baseline_pretrain.py:203). */
+int pf_stitch_accumulate(float* num, float* den, int32_t CH, int32_t CW, const float* tiles, int32_t T, int32_t th,
+                         int32_t tw, const int32_t* origins, const float* mask, int32_t up_h, int32_t up_w,
+                         void* stream);
+int pf_stitch_finalize(const float* num, const float* den, int64_t n, float* out, void* stream);
+/* RunningAverageMap.resize (utils.py:32-36): num' = nearest(avg) * bilinear_ac(cnt), den' = bilinear_ac(cnt) */
+int pf_stitch_resize(const float* num, const float* den, int32_t H, int32_t W, int32_t OH, int32_t OW, float* num_out,
+                     float* den_out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PF_B200_H_ */

@@ -1,0 +1,320 @@
+// Implicit-GEMM engine of the PatchFusion hot path (tcgen05 / TMEM / TMA, sm_100a).
+//
+// One persistent, warp-specialised kernel serves every dense contraction of the path:
+//   * ViT / Swin linear layers            (`dinov2/layers/attention.py:51,60`, `mlp.py:36-39`, `swin_layers.py:140,162`)
+//   * 1x1 convs (NHWC == plain GEMM)      (`depth_anything/dpt.py:30-38`, metric-head MLPs `localbins_layers.py:84-117`)
+//   * 3x3 stride-1 pad-1 convs over a channel-concat of up to three NHWC sources
+//                                          (`depth_anything/blocks.py:53-58`, `patchfusion.py:122-127,263-267`,
+//                                           `guided_fusion_model.py:34-69,98-99,203`)
+//   * ConvTranspose k==stride as GEMM + pixel-shuffle store (`depth_anything/dpt.py:40-53`)
+//
+// D[M,N] = sum_{src,tap,c} A_src[pixel(m)+tap, c] * Wp[n, k(src,tap,c)]   (bf16 x bf16 -> fp32 in TMEM)
+//
+// A tiles are fetched by TMA straight from the activation tensors: a 3x3 tap is just a (dx,dy) offset of the 4-D
+// box {64ch, bw, bh, 1} and the hardware zero-fills out-of-image pixels (conv padding), out-of-range channels and
+// rows, so there is no im2col buffer and no halo code.  Weights are pre-packed K-major [N, Ktot] with every
+// (source, tap) segment padded to a multiple of 64 channels, matching the producer's enumeration order.
+//
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM owner + single-thread tcgen05.mma issuer,
+// warps 2-5 = epilogue (TMEM -> registers -> bias / activation / residual / LayerScale -> global).
+// Two TMEM accumulator stages let the epilogue of tile i overlap the MMAs of tile i+1.
+#include "pf_common.cuh"
+#include "pf_kernels.h"
+
+namespace pf {
+
+constexpr int kBlockM = 128;
+constexpr int kBlockK = 64;
+constexpr int kATileBytes = kBlockM * kBlockK * 2;  // 16 KiB
+constexpr int kGemmThreads = 192;
+
+struct GemmKernelParams {
+  CUtensorMap tmA[3];
+  CUtensorMap tmB;
+  GemmDesc d;
+  int stages;
+  int total_tiles;
+  int k_steps;  // per tile
+};
+
+struct TileCoord {
+  int n0;               // first output column
+  int m0;               // linear: first row
+  int img, y0, x0;      // conv: tile origin
+};
+
+__device__ __forceinline__ TileCoord decode_tile(const GemmDesc& d, int t) {
+  TileCoord c;
+  int nt = t % d.n_tiles;
+  int mt = t / d.n_tiles;
+  c.n0 = nt * d.block_n;
+  c.m0 = mt * kBlockM;
+  c.img = 0; c.y0 = 0; c.x0 = 0;
+  if (d.a_mode == 1) {
+    int per_img = d.tiles_y * d.tiles_x;
+    c.img = mt / per_img;
+    int r = mt - c.img * per_img;
+    c.y0 = (r / d.tiles_x) * d.bh;
+    c.x0 = (r % d.tiles_x) * d.bw;
+  }
+  return c;
+}
+
+__device__ __forceinline__ float apply_act(float v, int act) {
+  if (act == PF_ACT_RELU) return fmaxf(v, 0.0f);
+  if (act == PF_ACT_GELU) return gelu_erf(v);
+  if (act == PF_ACT_SOFTPLUS) return softplus(v);
+  return v;
+}
+
+__global__ void __launch_bounds__(kGemmThreads, 1) pf_gemm_kernel(const __grid_constant__ GemmKernelParams P) {
+  extern __shared__ uint8_t smem_raw[];
+  const GemmDesc& d = P.d;
+  // 1024-B alignment is required by SWIZZLE_128B operand tiles.
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int stages = P.stages;
+  const int b_tile_bytes = d.block_n * kBlockK * 2;
+  const int stage_bytes = kATileBytes + b_tile_bytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + stages * stage_bytes);
+  uint64_t* empty_bar = full_bar + stages;
+  uint64_t* tmem_full = empty_bar + stages;   // [2]
+  uint64_t* tmem_empty = tmem_full + 2;       // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < d.num_src; ++s) prefetch_tmap(&P.tmA[s]);
+    prefetch_tmap(&P.tmB);
+    for (int s = 0; s < stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], 128); }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int t = blockIdx.x; t < P.total_tiles; t += gridDim.x) {
+        TileCoord c = decode_tile(d, t);
+        int kb = 0;  // running 64-wide K block index into the packed weights
+        for (int s = 0; s < d.num_src; ++s) {
+          for (int tap = 0; tap < d.taps; ++tap) {
+            int dy = d.taps == 9 ? tap / 3 - 1 : 0;
+            int dx = d.taps == 9 ? tap % 3 - 1 : 0;
+            for (int ch = 0; ch < d.chunks[s]; ++ch, ++kb) {
+              mbar_wait(&empty_bar[stage], phase ^ 1);
+              uint8_t* sa = smem + stage * stage_bytes;
+              uint8_t* sb = sa + kATileBytes;
+              mbar_expect_tx(&full_bar[stage], stage_bytes);
+              if (d.a_mode == 0) tma_load_2d(sa, &P.tmA[s], &full_bar[stage], ch * kBlockK, c.m0);
+              else tma_load_4d(sa, &P.tmA[s], &full_bar[stage], ch * kBlockK, c.x0 + dx, c.y0 + dy, c.img);
+              tma_load_2d(sb, &P.tmB, &full_bar[stage], kb * kBlockK, c.n0);
+              if (++stage == stages) { stage = 0; phase ^= 1; }
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc_bf16(kBlockM, d.block_n);
+      int stage = 0; uint32_t phase = 0;
+      int acc = 0; uint32_t acc_phase = 0;
+      for (int t = blockIdx.x; t < P.total_tiles; t += gridDim.x) {
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + acc * d.block_n;
+        for (int ks = 0; ks < P.k_steps; ++ks) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * stage_bytes);
+          const uint64_t adesc = umma_desc_k128(sa);
+          const uint64_t bdesc = umma_desc_k128(sa + kATileBytes);
+#pragma unroll
+          for (int k = 0; k < kBlockK / 16; ++k) {
+            // advance 16 bf16 = 32 B along K inside the 128-B swizzle row: +2 in the (addr>>4) field
+            umma_bf16(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (ks | k) != 0);
+          }
+          umma_commit(&empty_bar[stage]);            // frees this smem stage once the MMAs above retire
+          if (++stage == stages) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tmem_full[acc]);                // accumulator complete -> epilogue
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else {
+    // ===================== epilogue (warps 2..5) =====================
+    const int q = warp & 3;                 // TMEM lane quadrant this warp may access
+    const int r = q * 32 + lane;            // accumulator row owned by this thread
+    int acc = 0; uint32_t acc_phase = 0;
+    for (int t = blockIdx.x; t < P.total_tiles; t += gridDim.x) {
+      TileCoord c = decode_tile(d, t);
+      // ---- row mapping
+      bool row_ok;
+      long long orow;       // output row (pixel / token) index
+      if (d.a_mode == 1) {
+        int yy = r / d.bw, xx = r - yy * d.bw;
+        int y = c.y0 + yy, x = c.x0 + xx;
+        row_ok = (y < d.H) && (x < d.W);
+        orow = (static_cast<long long>(c.img) * d.H + y) * d.W + x;
+      } else {
+        int m = c.m0 + r;
+        row_ok = m < d.M;
+        orow = m;
+      }
+      int ocol0 = c.n0;     // output column of accumulator column 0
+      if (d.ps > 1 && d.a_mode == 0) {
+        // ConvTranspose k==s: columns are ordered (ky, kx, cout); this N tile belongs to one (ky,kx).
+        int tap = c.n0 / d.ps_cout;
+        ocol0 = c.n0 - tap * d.ps_cout;
+        int ky = tap / d.ps, kx = tap - ky * d.ps;
+        int m = c.m0 + r;
+        int img = m / (d.H * d.W);
+        int rem = m - img * d.H * d.W;
+        int y = rem / d.W, x = rem - y * d.W;
+        orow = (static_cast<long long>(img) * d.H * d.ps + y * d.ps + ky) * (d.W * d.ps) + x * d.ps + kx;
+      }
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * d.block_n;
+      for (int cb = 0; cb < d.block_n; cb += 32) {
+        uint32_t v[32];
+        tmem_ld32(taddr + cb, v);
+        tmem_ld_wait();
+        if (row_ok) {
+          const int ncol = c.n0 + cb;            // accumulator/global N index of v[0]
+          const int oc = ocol0 + cb + d.out_col0;
+          float f[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            float x = __uint_as_float(v[j]);
+            if (d.bias != nullptr && ncol + j < d.N) x += __ldg(d.bias + ncol + j);
+            f[j] = apply_act(x, d.act);
+          }
+          if (d.res1 != nullptr) {
+            const __nv_bfloat16* rp = d.res1 + orow * d.res_ld + (ocol0 + cb);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) if (ncol + j < d.N) f[j] += __bfloat162float(rp[j]);
+          }
+          if (d.res2 != nullptr) {
+            const __nv_bfloat16* rp = d.res2 + orow * d.res_ld + (ocol0 + cb);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) if (ncol + j < d.N) f[j] += __bfloat162float(rp[j]);
+          }
+          if (d.vt != nullptr && ncol >= d.vt_col0) {
+            // attention V written transposed: vt[(b*heads + h)*64 + dd][token]
+            int m = static_cast<int>(orow);
+            int b = m / d.vt_seq, tok = m - b * d.vt_seq;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              int cc = ncol + j - d.vt_col0;      // h*64 + dd
+              if (ncol + j < d.N)
+                d.vt[(static_cast<long long>(b) * d.vt_dim + cc) * d.vt_seq_pad + tok] = __float2bfloat16(f[j]);
+            }
+          } else if (d.gamma != nullptr) {
+            // x <- x + gamma * (acc + bias): fp32 residual stream updated in place
+            float* xp = reinterpret_cast<float*>(d.out) + orow * d.out_ld + oc;
+            if (ncol + 32 <= d.N) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) {
+                float4 xv = *reinterpret_cast<float4*>(xp + j);
+                float4 g = __ldg(reinterpret_cast<const float4*>(d.gamma + ncol + j));
+                xv.x += g.x * f[j]; xv.y += g.y * f[j + 1]; xv.z += g.z * f[j + 2]; xv.w += g.w * f[j + 3];
+                *reinterpret_cast<float4*>(xp + j) = xv;
+              }
+            } else {
+              for (int j = 0; j < 32; ++j) if (ncol + j < d.N) xp[j] += __ldg(d.gamma + ncol + j) * f[j];
+            }
+          } else if (d.out_f32) {
+            float* op = reinterpret_cast<float*>(d.out) + orow * d.out_ld + oc;
+            if (ncol + 32 <= d.N) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 4)
+                *reinterpret_cast<float4*>(op + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+            } else {
+              for (int j = 0; j < 32; ++j) if (ncol + j < d.N) op[j] = f[j];
+            }
+          } else {
+            __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(d.out) + orow * d.out_ld + oc;
+            if (ncol + 32 <= d.N) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 8) {
+                uint4 pk = make_uint4(pack_bf16(f[j], f[j + 1]), pack_bf16(f[j + 2], f[j + 3]),
+                                      pack_bf16(f[j + 4], f[j + 5]), pack_bf16(f[j + 6], f[j + 7]));
+                *reinterpret_cast<uint4*>(op + j) = pk;
+              }
+            } else {
+              for (int j = 0; j < 32; ++j) if (ncol + j < d.N) op[j] = __float2bfloat16(f[j]);
+            }
+            if (d.out2 != nullptr) {
+              __nv_bfloat16* o2 = d.out2 + orow * d.out2_ld + (ocol0 + cb);
+              for (int j = 0; j < 32; ++j) if (ncol + j < d.N) o2[j] = __float2bfloat16(fmaxf(f[j], 0.0f));
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&tmem_empty[acc]);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------------------
+static int g_sm_count = 0;
+
+int gemm_launch(const GemmDesc& d, const CUtensorMap* tmA, const CUtensorMap& tmB, cudaStream_t stream) {
+  static bool attr_done = false;
+  const int kMaxSmem = 227 * 1024;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(pf_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
+    if (e != cudaSuccess) return set_error("cudaFuncSetAttribute(pf_gemm_kernel): %s", cudaGetErrorString(e));
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev);
+    attr_done = true;
+  }
+  if (d.block_n % 32 != 0 || d.block_n < 32 || d.block_n > 256) return set_error("gemm: bad block_n %d", d.block_n);
+  GemmKernelParams P;
+  for (int s = 0; s < d.num_src; ++s) P.tmA[s] = tmA[s];
+  for (int s = d.num_src; s < 3; ++s) P.tmA[s] = tmA[0];
+  P.tmB = tmB;
+  P.d = d;
+  int stage_bytes = kATileBytes + d.block_n * kBlockK * 2;
+  int budget = kMaxSmem - 1024 /*align*/ - 256 /*barriers*/;
+  int stages = budget / stage_bytes;
+  if (stages > 8) stages = 8;
+  if (stages < 2) return set_error("gemm: not enough shared memory for 2 stages");
+  P.stages = stages;
+  int ks = 0;
+  for (int s = 0; s < d.num_src; ++s) ks += d.chunks[s] * d.taps;
+  P.k_steps = ks;
+  P.total_tiles = d.m_tiles * d.n_tiles;
+  if (P.total_tiles <= 0 || ks <= 0) return set_error("gemm: empty problem");
+  int grid = P.total_tiles < g_sm_count ? P.total_tiles : g_sm_count;
+  size_t smem = 1024 + static_cast<size_t>(stages) * stage_bytes + 256;
+  pf_gemm_kernel<<<grid, kGemmThreads, smem, stream>>>(P);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_error("pf_gemm_kernel launch: %s", cudaGetErrorString(e));
+  count_launch();
+  return 0;
+}
+
+}  // namespace pf

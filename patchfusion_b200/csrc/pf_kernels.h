@@ -1,0 +1,45 @@
+// Internal declarations shared by the translation units of libpf_b200.so.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include "../../include/pf_b200.h"
+
+namespace pf {
+
+// Kernel-side view of pf_gemm_desc (device pointers typed, host-only fields dropped).
+struct GemmDesc {
+  int num_src, a_mode, taps;
+  int chunks[3];
+  int M, NB, H, W, bh, bw, tiles_y, tiles_x, m_tiles;
+  int N, block_n, n_tiles;
+  const float* bias;
+  int act;
+  const __nv_bfloat16* res1;
+  const __nv_bfloat16* res2;
+  int res_ld;
+  const float* gamma;
+  void* out;
+  int out_f32, out_ld, out_col0;
+  __nv_bfloat16* out2;
+  int out2_ld;
+  int ps, ps_cout;
+  __nv_bfloat16* vt;
+  int vt_col0, vt_seq, vt_seq_pad, vt_dim;
+};
+
+int set_error(const char* fmt, ...);
+void count_launch();
+int check_launch(const char* what);
+
+int gemm_launch(const GemmDesc& d, const CUtensorMap* tmA, const CUtensorMap& tmB, cudaStream_t stream);
+
+// Tensor maps (driver entry point fetched at run time; cached by key).
+int tmap_2d_bf16(CUtensorMap* out, const void* ptr, uint64_t cols, uint64_t rows, uint64_t ld_elems, uint32_t box_cols,
+                 uint32_t box_rows);
+int tmap_3d_bf16(CUtensorMap* out, const void* ptr, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t ld1_elems,
+                 uint64_t ld2_elems, uint32_t b0, uint32_t b1, uint32_t b2);
+int tmap_4d_nhwc_bf16(CUtensorMap* out, const void* ptr, uint64_t C, uint64_t W, uint64_t H, uint64_t N,
+                      uint64_t ld_elems, uint32_t box_c, uint32_t box_w, uint32_t box_h);
+
+}  // namespace pf

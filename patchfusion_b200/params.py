@@ -1,0 +1,295 @@
+"""State-dict layout, parameter tree and synthetic weights for the PatchFusion hot path.
+
+The drop-in contract is that a checkpoint written by the reference
+(`estimator/models/patchfusion.py:57-173`, HF `from_pretrained`) loads into this package unchanged.  The layout
+is therefore restated here as data: `state_layout(config)` yields every key, shape and dtype in the order the
+reference's `state_dict()` emits them; `ParamTree` materialises it as nested `nn.Module` containers (so
+`state_dict()/load_state_dict()/to()` behave like the reference module), and `synthetic_state_dict` fills it with
+seeded, variance-preserving random weights (no network, no checkpoints in this environment).
+
+tests/test_layout.py checks the layout against tests/golden/state_dict_layout_{vits,vitl}.json, which were dumped
+from the reference itself by oracle/make_golden.py.
+"""
+from collections import OrderedDict
+import math
+
+import torch
+import torch.nn as nn
+
+# DINOv2 encoders as instantiated by hubconf (`hubconf.py:24-67`, `vision_transformer.py:339-378`) and the DPT
+# widths chosen in `zoedepth/models/base_models/depth_anything.py:345-353`.
+ENCODERS = {
+    'vits': dict(dim=384, depth=12, heads=6, out_channels=[48, 96, 192, 384], features=64),
+    'vitb': dict(dim=768, depth=12, heads=12, out_channels=[96, 192, 384, 768], features=128),
+    'vitl': dict(dim=1024, depth=24, heads=16, out_channels=[256, 512, 1024, 1024], features=256),
+}
+PATCH = 14
+POS_GRID = 37          # 518 / 14: pos_embed holds 1 + 37*37 entries (`hubconf.py:38`, img_size=518)
+N_MIDAS_OUT = 32       # `patchfusion.py:119`, `zoedepth_v1.py:79`
+WINDOW = 12            # `guided_fusion_model.py:133`
+G2L_DEPTH = [2, 2, 3, 3, 4, 4]          # high -> low resolution (`guided_fusion_model.py:109`)
+G2L_HEADS = [8, 8, 16, 16, 32, 32]      # (`guided_fusion_model.py:110`)
+
+
+def _get(cfg, key, default=None):
+    if isinstance(cfg, dict):
+        return cfg.get(key, default)
+    return getattr(cfg, key, default)
+
+
+def branch_hparams(branch_cfg):
+    enc = _get(branch_cfg, 'midas_model_type')
+    if enc not in ENCODERS:
+        raise NotImplementedError(
+            "backbone %r is not vendored in the reference tree (only Depth-Anything vits/vitb/vitl are; the "
+            "ZoeDepth-N BEiT-L backbone comes from an un-vendored torch.hub repo, SURVEY.md §8c)" % (enc,))
+    hp = dict(ENCODERS[enc])
+    hp['encoder'] = enc
+    hp['n_bins'] = _get(branch_cfg, 'n_bins', 64)
+    hp['bin_embedding_dim'] = _get(branch_cfg, 'bin_embedding_dim', 128)
+    hp['n_attractors'] = list(_get(branch_cfg, 'n_attractors', [16, 8, 4, 1]))
+    hp['bin_centers_type'] = _get(branch_cfg, 'bin_centers_type', 'softplus')
+    if hp['bin_centers_type'] not in ('normed', 'softplus', 'hybrid1', 'hybrid2'):
+        raise ValueError("bin_centers_type should be one of 'normed', 'softplus', 'hybrid1', 'hybrid2'")
+    if hp['bin_centers_type'] != 'softplus':
+        raise NotImplementedError("only bin_centers_type='softplus' (every shipped PatchFusion config) is built")
+    return hp
+
+
+def _f(shape):
+    return (tuple(shape), torch.float32, 'param')
+
+
+def _conv(L, name, cout, cin, k, bias=True):
+    L[name + '.weight'] = _f((cout, cin, k, k))
+    if bias:
+        L[name + '.bias'] = _f((cout,))
+
+
+def _linear(L, name, cout, cin):
+    L[name + '.weight'] = _f((cout, cin))
+    L[name + '.bias'] = _f((cout,))
+
+
+def _norm(L, name, c):
+    L[name + '.weight'] = _f((c,))
+    L[name + '.bias'] = _f((c,))
+
+
+def _bn(L, name, c):
+    L[name + '.weight'] = _f((c,))
+    L[name + '.bias'] = _f((c,))
+    L[name + '.running_mean'] = ((c,), torch.float32, 'buffer')
+    L[name + '.running_var'] = ((c,), torch.float32, 'buffer')
+    L[name + '.num_batches_tracked'] = ((), torch.int64, 'buffer')
+
+
+def _metric_head(L, pre, C, hp):
+    """seed regressor / projectors / attractors / conditional log-binomial (`zoedepth_v1.py:103-123`,
+    `patchfusion.py:149-170`)."""
+    E = hp['bin_embedding_dim']
+    _conv(L, pre + 'seed_bin_regressor._net.0', 256, C, 1)
+    _conv(L, pre + 'seed_bin_regressor._net.2', hp['n_bins'], 256, 1)
+    _conv(L, pre + 'seed_projector._net.0', 128, C, 1)
+    _conv(L, pre + 'seed_projector._net.2', E, 128, 1)
+    for i in range(4):
+        _conv(L, pre + 'projectors.%d._net.0' % i, 128, C, 1)
+        _conv(L, pre + 'projectors.%d._net.2' % i, E, 128, 1)
+    for i in range(4):
+        _conv(L, pre + 'attractors.%d._net.0' % i, 128, E, 1)
+        _conv(L, pre + 'attractors.%d._net.2' % i, hp['n_attractors'][i], 128, 1)
+    L[pre + 'conditional_log_binomial.log_binomial_transform.k_idx'] = ((1, hp['n_bins'], 1, 1), torch.int64, 'buffer')
+    L[pre + 'conditional_log_binomial.log_binomial_transform.K_minus_1'] = ((1, 1, 1, 1), torch.float32, 'buffer')
+    cin = N_MIDAS_OUT + 1 + E
+    _conv(L, pre + 'conditional_log_binomial.mlp.0', cin // 2, cin, 1)
+    _conv(L, pre + 'conditional_log_binomial.mlp.2', 4, cin // 2, 1)
+
+
+def _branch(L, pre, hp):
+    D, C, oc = hp['dim'], hp['features'], hp['out_channels']
+    vit = pre + 'core.core.pretrained.'
+    L[vit + 'cls_token'] = _f((1, 1, D))
+    L[vit + 'pos_embed'] = _f((1, 1 + POS_GRID * POS_GRID, D))
+    L[vit + 'mask_token'] = _f((1, D))
+    _conv(L, vit + 'patch_embed.proj', D, 3, PATCH)
+    for b in range(hp['depth']):
+        p = vit + 'blocks.%d.' % b
+        _norm(L, p + 'norm1', D)
+        _linear(L, p + 'attn.qkv', 3 * D, D)
+        _linear(L, p + 'attn.proj', D, D)
+        L[p + 'ls1.gamma'] = _f((D,))
+        _norm(L, p + 'norm2', D)
+        _linear(L, p + 'mlp.fc1', 4 * D, D)
+        _linear(L, p + 'mlp.fc2', D, 4 * D)
+        L[p + 'ls2.gamma'] = _f((D,))
+    _norm(L, vit + 'norm', D)
+    dh = pre + 'core.core.depth_head.'
+    for i in range(4):
+        _conv(L, dh + 'projects.%d' % i, oc[i], D, 1)
+    _conv(L, dh + 'resize_layers.0', oc[0], oc[0], 4)   # ConvTranspose2d k4 s4: weight (in, out, 4, 4)
+    _conv(L, dh + 'resize_layers.1', oc[1], oc[1], 2)   # ConvTranspose2d k2 s2
+    _conv(L, dh + 'resize_layers.3', oc[3], oc[3], 3)   # Conv2d k3 s2 p1
+    for i in range(4):
+        _conv(L, dh + 'scratch.layer%d_rn' % (i + 1), C, oc[i], 3, bias=False)
+    for i in range(1, 5):
+        r = dh + 'scratch.refinenet%d.' % i
+        _conv(L, r + 'out_conv', C, C, 1)
+        for u in (1, 2):
+            _conv(L, r + 'resConfUnit%d.conv1' % u, C, C, 3)
+            _conv(L, r + 'resConfUnit%d.conv2' % u, C, C, 3)
+    _conv(L, dh + 'scratch.output_conv1', C // 2, C, 3)
+    _conv(L, dh + 'scratch.output_conv2.0', N_MIDAS_OUT, C // 2, 3)
+    _conv(L, dh + 'scratch.output_conv2.2', 1, N_MIDAS_OUT, 1)
+    _conv(L, pre + 'conv2', C, C, 1)
+    _metric_head(L, pre, C, hp)
+
+
+def guided_fusion_hparams(gf_cfg, patch_process_shape):
+    in_ch = list(_get(gf_cfg, 'in_channels', [32, 256, 256, 256, 256, 256]))
+    num_patches = list(_get(gf_cfg, 'num_patches',
+                            [384 * 512, 192 * 256, 96 * 128, 48 * 64, 24 * 32, 12 * 16]))
+    return dict(in_channels=in_ch, num_patches=num_patches, n_channels=_get(gf_cfg, 'n_channels', 5),
+                depth=list(_get(gf_cfg, 'depth', G2L_DEPTH)), num_heads=list(_get(gf_cfg, 'num_heads', G2L_HEADS)))
+
+
+def state_layout(config):
+    """OrderedDict key -> (shape, dtype, 'param'|'buffer') in the reference's `state_dict()` order."""
+    hp_c = branch_hparams(_get(config, 'coarse_branch'))
+    hp_f = branch_hparams(_get(config, 'fine_branch'))
+    gf = guided_fusion_hparams(_get(config, 'guided_fusion'), _get(config, 'patch_process_shape'))
+    L = OrderedDict()
+    _branch(L, 'coarse_branch.', hp_c)
+    _branch(L, 'fine_branch.', hp_f)
+    C = hp_f['features']
+    for i in range(6):
+        c = N_MIDAS_OUT if i == 5 else C
+        _conv(L, 'fusion_conv_list.%d' % i, c, 2 * c, 3)
+    ic = gf['in_channels']
+    g = 'guided_fusion.'
+
+    def double_conv_bn(pre, cin, cout):
+        _conv(L, pre + 'double_conv.0', cout, cin, 3, bias=False)
+        _bn(L, pre + 'double_conv.1', cout)
+        _conv(L, pre + 'double_conv.3', cout, cout, 3, bias=False)
+        _bn(L, pre + 'double_conv.4', cout)
+
+    def double_conv(pre, cin, cmid, cout):
+        _conv(L, pre + 'double_conv.0', cmid, cin, 3)
+        _conv(L, pre + 'double_conv.2', cout, cmid, 3)
+
+    double_conv_bn(g + 'inc.', gf['n_channels'], ic[0])
+    for i in range(5):
+        double_conv_bn(g + 'down_conv_list.%d.maxpool_conv.1.' % i, ic[i], ic[i + 1])
+    inv = ic[::-1]
+    for i in range(1, 6):
+        cin = inv[i] + 2 * inv[i - 1]
+        double_conv(g + 'up_conv_list.%d.conv.' % (i - 1), cin, cin, inv[i])
+    depth_inv, heads_inv, np_inv = gf['depth'][::-1], gf['num_heads'][::-1], gf['num_patches'][::-1]
+    for i in range(6):
+        c, p = inv[i], g + 'g2l_list.%d.' % i
+        L[p + 'absolute_pos_embed'] = _f((1, np_inv[i], c))
+        for b in range(depth_inv[i]):
+            q = p + 'g2l_layer.blocks.%d.' % b
+            _norm(L, q + 'norm1', c)
+            L[q + 'attn.relative_position_bias_table'] = _f(((2 * WINDOW - 1) ** 2, heads_inv[i]))
+            L[q + 'attn.relative_position_index'] = ((WINDOW * WINDOW, WINDOW * WINDOW), torch.int64, 'buffer')
+            _linear(L, q + 'attn.qkv', 3 * c, c)
+            _linear(L, q + 'attn.proj', c, c)
+            _norm(L, q + 'norm2', c)
+            _linear(L, q + 'mlp.fc1', 4 * c, c)
+            _linear(L, q + 'mlp.fc2', c, 4 * c)
+        _norm(L, p + 'g2l_layer_norm', c)
+        _conv(L, p + 'embed_proj', c, 1, 1)
+    for i in range(6):
+        double_conv(g + 'convs.%d.' % i, 2 * inv[i], inv[i], inv[i])
+    _metric_head(L, '', C, hp_c)
+    return L
+
+
+def relative_position_index(ws=WINDOW):
+    """Swin relative-position lookup (`swin_layers.py:108-118`): index (i, j) -> row of the (2ws-1)^2 bias table."""
+    ys, xs = torch.meshgrid(torch.arange(ws), torch.arange(ws), indexing='ij')
+    co = torch.stack([ys.flatten(), xs.flatten()])               # 2, ws*ws
+    rel = co[:, :, None] - co[:, None, :] + (ws - 1)              # 2, N, N  in [0, 2ws-2]
+    return rel[0] * (2 * ws - 1) + rel[1]
+
+
+class _Node(nn.Module):
+    """Pure container; exists so dotted state-dict paths map onto sub-modules."""
+
+
+class ParamTree(nn.Module):
+    """Base class materialising `state_layout(config)` as parameters/buffers at the reference's dotted paths."""
+
+    def _build_tree(self, layout):
+        for key, (shape, dtype, kind) in layout.items():
+            parts = key.split('.')
+            node = self
+            for p in parts[:-1]:
+                if p not in node._modules:
+                    node.add_module(p, _Node())
+                node = node._modules[p]
+            t = torch.zeros(shape, dtype=dtype)
+            if kind == 'param':
+                node.register_parameter(parts[-1], nn.Parameter(t, requires_grad=False))
+            else:
+                node.register_buffer(parts[-1], t)
+
+
+def synthetic_state_dict(config, seed=0, dtype=torch.float32):
+    """Seeded random weights with O(1) activations through the whole network.
+
+    Linear/conv weights ~ N(0, gain/fan_in); the residual branches of the ViT/Swin blocks and the DPT RCUs are
+    scaled down so the stream does not blow up; BN stats near identity; position tables small.  The values are a
+    function of (key order, shapes, seed) only, so the GPU box regenerates exactly the weights the oracle and the
+    golden fixtures were produced with.
+    """
+    g = torch.Generator().manual_seed(seed)
+    layout = state_layout(config)
+    sd = OrderedDict()
+
+    def rn(shape, std):
+        return torch.randn(shape, generator=g, dtype=torch.float32) * std
+
+    for key, (shape, dt, kind) in layout.items():
+        leaf = key.split('.')[-1]
+        if key.endswith('relative_position_index'):
+            t = relative_position_index()
+        elif leaf == 'k_idx':
+            t = torch.arange(shape[1]).view(shape)
+        elif leaf == 'K_minus_1':
+            t = torch.full(shape, float(layout[key.replace('K_minus_1', 'k_idx')][0][1] - 1))
+        elif leaf == 'num_batches_tracked':
+            t = torch.zeros((), dtype=torch.int64)
+        elif leaf == 'running_mean':
+            t = rn(shape, 0.1)
+        elif leaf == 'running_var':
+            t = 1.0 + 0.2 * torch.rand(shape, generator=g)
+        elif leaf == 'gamma':                                    # LayerScale
+            t = 0.3 + 0.1 * torch.rand(shape, generator=g)
+        elif leaf in ('cls_token', 'mask_token'):
+            t = rn(shape, 0.5)
+        elif leaf == 'pos_embed' or leaf == 'absolute_pos_embed':
+            t = rn(shape, 0.3)
+        elif leaf == 'relative_position_bias_table':
+            t = rn(shape, 0.5)
+        elif leaf == 'bias':
+            t = rn(shape, 0.05)
+        elif leaf == 'weight' and len(shape) == 1:               # LayerNorm / BatchNorm scale
+            t = 1.0 + rn(shape, 0.1)
+        elif leaf == 'weight':
+            fan_in = 1
+            for s in shape[1:]:
+                fan_in *= s
+            if 'resize_layers.0' in key or 'resize_layers.1' in key:
+                fan_in = shape[0]                                # ConvTranspose k==s: one tap per output pixel
+            gain = 2.0 if ('conv' in key or '_net' in key or 'fusion' in key or 'depth_head' in key) else 1.0
+            if 'resConfUnit' in key and key.endswith('conv2.weight'):
+                gain = 0.5
+            if key.endswith('_net.2.weight') and 'attractors' in key:
+                gain = 4.0
+            t = rn(shape, math.sqrt(gain / fan_in))
+        else:
+            raise AssertionError(key)
+        sd[key] = t.to(dt if dt != torch.float32 else dtype)
+    return sd
