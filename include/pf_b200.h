@@ -77,7 +77,8 @@ int pf_gemm(pf_gemm_desc* desc, void* stream);
  *   scale (nullable, [N]): per-output-channel factor folded into the weights (eval-mode BatchNorm). */
 int pf_pack_weight(const float* w, int32_t N, int32_t N_pad, int32_t num_src, const int32_t* src_c, int32_t taps,
                    const float* scale, void* dst, void* stream);
-/* ConvTranspose2d(k==s) weight [Cin, Cout, k, k] -> [k*k*Cout, Cin_pad] bf16, row = (ky*k + kx)*Cout + co. */
+/* ConvTranspose2d(k==s) weight [Cin, Cout, k, k] -> [k*k*Cp, Cin_pad64] bf16, Cp = pad32(Cout),
+ * row = (ky*k + kx)*Cp + co (rows co >= Cout are zero).  Use with pf_gemm ps=k, ps_cout=Cout, N=k*k*Cp. */
 int pf_pack_weight_convT(const float* w, int32_t Cin, int32_t Cout, int32_t k, void* dst, void* stream);
 
 /* ---- ViT pieces --------------------------------------------------------------------------------------------- */
@@ -146,11 +147,12 @@ int pf_swin_residual_crop(float* x, const float* y, int32_t H, int32_t W, int32_
 /* x = emb + up(prev_emb) (attractor.py:175-178), NHWC bf16 */
 int pf_add_upsampled(const void* a, int32_t B, int32_t H, int32_t W, int32_t C, const void* prev, int32_t PH,
                      int32_t PW, void* out, void* stream);
-/* b_new = up(b_prev) + mean_a inv_attractor(A_a - up(b_prev)), alpha=300, gamma=2; fp32 [B,H,W,nbins] */
-int pf_attractor(const float* A, int32_t nA, const float* b_prev, int32_t PH, int32_t PW, int32_t B, int32_t H,
+/* b_new = up(b_prev) + mean_a inv_attractor(A_a - up(b_prev)), alpha=300, gamma=2; fp32 [B,H,W,nbins];
+ * A: fp32 [B*H*W, A_ld] (first nA columns used) */
+int pf_attractor(const float* A, int32_t A_ld, int32_t nA, const float* b_prev, int32_t PH, int32_t PW, int32_t B, int32_t H,
                  int32_t W, int32_t nbins, int32_t kind_mean, float* b_out, void* stream);
 /* depth = sum_k softmax_k(logbinom(p)/t) * up(b_centers)_k from the 4-channel softplus'd pt map */
-int pf_logbinom_depth(const float* pt, const float* b_centers, int32_t BH, int32_t BW, int32_t B, int32_t H, int32_t W,
+int pf_logbinom_depth(const float* pt, int32_t pt_ld, const float* b_centers, int32_t BH, int32_t BW, int32_t B, int32_t H, int32_t W,
                       int32_t nbins, float min_temp, float max_temp, float* depth, void* stream);
 
 /* ---- stitch (baseline_pretrain.py:310-326, estimator/models/utils.py:21-36 in closed form) --------------------- */

@@ -1,0 +1,747 @@
+// HBM-bound kernels of the PatchFusion hot path: normalisation, resampling, ROI crop-zoom, pooling, token assembly,
+// Swin window attention (tiny head_dim -> CUDA cores), the metric-bins tail and the scatter-stitch.
+// Layout: activations NHWC bf16 (row stride `ld`), 8 channels (16 B) per thread where the op is per-pixel.
+#include "pf_common.cuh"
+#include "pf_kernels.h"
+
+namespace pf {
+
+typedef __nv_bfloat16 bf16;
+
+__device__ __forceinline__ void unpack8(const uint4& u, float* f) {
+  const __nv_bfloat162* p = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { float2 t = __bfloat1622float2(p[i]); f[2 * i] = t.x; f[2 * i + 1] = t.y; }
+}
+__device__ __forceinline__ uint4 pack8(const float* f) {
+  return make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+static inline unsigned nblocks(long long n, int threads) { return static_cast<unsigned>((n + threads - 1) / threads); }
+
+// ------------------------------------------------------------------------------------------------ LayerNorm
+// one warp per row; two-pass (mean, then centred variance) in fp32 like ATen.
+__global__ void layernorm_kernel(const float* __restrict__ x, int x_ld, const float* __restrict__ w,
+                                 const float* __restrict__ b, float eps, int rows, int C, bf16* __restrict__ out,
+                                 int out_ld) {
+  int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const float* xr = x + static_cast<long long>(row) * x_ld;
+  float s = 0.f;
+  for (int c = lane * 4; c < C; c += 128) { float4 v = *reinterpret_cast<const float4*>(xr + c); s += v.x + v.y + v.z + v.w; }
+  float mean = warp_sum(s) / C;
+  float q = 0.f;
+  for (int c = lane * 4; c < C; c += 128) {
+    float4 v = *reinterpret_cast<const float4*>(xr + c);
+    float a = v.x - mean, bb = v.y - mean, cc = v.z - mean, d = v.w - mean;
+    q += a * a + bb * bb + cc * cc + d * d;
+  }
+  float rstd = rsqrtf(warp_sum(q) / C + eps);
+  bf16* orow = out + static_cast<long long>(row) * out_ld;
+  for (int c = lane * 4; c < C; c += 128) {
+    float4 v = *reinterpret_cast<const float4*>(xr + c);
+    float4 g = *reinterpret_cast<const float4*>(w + c);
+    float4 be = *reinterpret_cast<const float4*>(b + c);
+    uint2 pk = make_uint2(pack_bf16((v.x - mean) * rstd * g.x + be.x, (v.y - mean) * rstd * g.y + be.y),
+                          pack_bf16((v.z - mean) * rstd * g.z + be.z, (v.w - mean) * rstd * g.w + be.w));
+    *reinterpret_cast<uint2*>(orow + c) = pk;
+  }
+}
+
+// LayerNorm into the zero-padded (Hp x Wp) Swin token grid.
+__global__ void swin_norm_pad_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                     const float* __restrict__ b, float eps, int H, int W, int Hp, int Wp, int C,
+                                     bf16* __restrict__ out) {
+  int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  int lane = threadIdx.x & 31;
+  if (row >= Hp * Wp) return;
+  int y = row / Wp, xx = row - y * Wp;
+  bf16* orow = out + static_cast<long long>(row) * C;
+  if (y >= H || xx >= W) {
+    for (int c = lane * 4; c < C; c += 128) *reinterpret_cast<uint2*>(orow + c) = make_uint2(0u, 0u);
+    return;
+  }
+  const float* xr = x + (static_cast<long long>(y) * W + xx) * C;
+  float s = 0.f;
+  for (int c = lane * 4; c < C; c += 128) { float4 v = *reinterpret_cast<const float4*>(xr + c); s += v.x + v.y + v.z + v.w; }
+  float mean = warp_sum(s) / C;
+  float q = 0.f;
+  for (int c = lane * 4; c < C; c += 128) {
+    float4 v = *reinterpret_cast<const float4*>(xr + c);
+    float a = v.x - mean, bb = v.y - mean, cc = v.z - mean, d = v.w - mean;
+    q += a * a + bb * bb + cc * cc + d * d;
+  }
+  float rstd = rsqrtf(warp_sum(q) / C + eps);
+  for (int c = lane * 4; c < C; c += 128) {
+    float4 v = *reinterpret_cast<const float4*>(xr + c);
+    float4 g = *reinterpret_cast<const float4*>(w + c);
+    float4 be = *reinterpret_cast<const float4*>(b + c);
+    uint2 pk = make_uint2(pack_bf16((v.x - mean) * rstd * g.x + be.x, (v.y - mean) * rstd * g.y + be.y),
+                          pack_bf16((v.z - mean) * rstd * g.z + be.z, (v.w - mean) * rstd * g.w + be.w));
+    *reinterpret_cast<uint2*>(orow + c) = pk;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ ViT input
+__global__ void patch_im2col_kernel(const float* __restrict__ img, int B, int H, int W, bf16* __restrict__ out, int ld) {
+  const int gh = H / 14, gw = W / 14;
+  long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  long long total = static_cast<long long>(B) * gh * gw * ld;
+  if (idx >= total) return;
+  int col = static_cast<int>(idx % ld);
+  long long row = idx / ld;
+  float v = 0.f;
+  if (col < 588) {
+    int c = col / 196, rr = col - c * 196, py = rr / 14, px = rr - py * 14;
+    int gx = static_cast<int>(row % gw);
+    long long t = row / gw;
+    int gy = static_cast<int>(t % gh);
+    int b = static_cast<int>(t / gh);
+    const float mean[3] = {0.485f, 0.456f, 0.406f}, stdv[3] = {0.229f, 0.224f, 0.225f};
+    float p = img[((static_cast<long long>(b) * 3 + c) * H + gy * 14 + py) * W + gx * 14 + px];
+    v = (p - mean[c]) / stdv[c];
+  }
+  out[idx] = __float2bfloat16(v);
+}
+
+__global__ void assemble_tokens_kernel(const float* __restrict__ patch, const float* __restrict__ cls,
+                                       const float* __restrict__ pos, int B, int n_patch, int D,
+                                       float* __restrict__ tokens) {
+  long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  long long total = static_cast<long long>(B) * (n_patch + 1) * D;
+  if (idx >= total) return;
+  int d = static_cast<int>(idx % D);
+  long long t = idx / D;
+  int tok = static_cast<int>(t % (n_patch + 1));
+  int b = static_cast<int>(t / (n_patch + 1));
+  float v = tok == 0 ? cls[d] : patch[(static_cast<long long>(b) * n_patch + tok - 1) * D + d];
+  tokens[idx] = v + pos[static_cast<long long>(tok) * D + d];
+}
+
+__global__ void f32_to_bf16_kernel(const float* __restrict__ in, long long n, bf16* __restrict__ out) {
+  long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (i < n) out[i] = __float2bfloat16(in[i]);
+}
+
+// ------------------------------------------------------------------------------------------------ resampling
+// align_corners=True source coordinate exactly as ATen: scale = (in-1)/(out-1) (0 when out == 1), src = scale*dst.
+__device__ __forceinline__ void ac_coord(int dst, int in, int out, int& lo, int& hi, float& frac) {
+  float scale = out > 1 ? static_cast<float>(in - 1) / static_cast<float>(out - 1) : 0.f;
+  float src = scale * dst;
+  lo = static_cast<int>(src);
+  if (lo > in - 1) lo = in - 1;
+  hi = lo + (lo < in - 1 ? 1 : 0);
+  frac = src - lo;
+}
+
+__global__ void resize_bilinear_kernel(const bf16* __restrict__ in, int B, int H, int W, int C, int in_ld, int OH,
+                                       int OW, bf16* __restrict__ out, int out_ld, int out_col0) {
+  const int cg = C >> 3;
+  long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  long long total = static_cast<long long>(B) * OH * OW * cg;
+  if (idx >= total) return;
+  int g = static_cast<int>(idx % cg);
+  long long p = idx / cg;
+  int ox = static_cast<int>(p % OW);
+  long long t = p / OW;
+  int oy = static_cast<int>(t % OH);
+  int b = static_cast<int>(t / OH);
+  int y0, y1, x0, x1; float fy, fx;
+  ac_coord(oy, H, OH, y0, y1, fy);
+  ac_coord(ox, W, OW, x0, x1, fx);
+  const bf16* base = in + static_cast<long long>(b) * H * W * in_ld + g * 8;
+  float a[8], bb[8], c[8], d[8], o[8];
+  unpack8(*reinterpret_cast<const uint4*>(base + (static_cast<long long>(y0) * W + x0) * in_ld), a);
+  unpack8(*reinterpret_cast<const uint4*>(base + (static_cast<long long>(y0) * W + x1) * in_ld), bb);
+  unpack8(*reinterpret_cast<const uint4*>(base + (static_cast<long long>(y1) * W + x0) * in_ld), c);
+  unpack8(*reinterpret_cast<const uint4*>(base + (static_cast<long long>(y1) * W + x1) * in_ld), d);
+  const float w00 = (1.f - fy) * (1.f - fx), w01 = (1.f - fy) * fx, w10 = fy * (1.f - fx), w11 = fy * fx;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) o[i] = w00 * a[i] + w01 * bb[i] + w10 * c[i] + w11 * d[i];
+  *reinterpret_cast<uint4*>(out + p * out_ld + out_col0 + g * 8) = pack8(o);
+}
+
+__global__ void resize_bilinear_f32_kernel(const float* __restrict__ in, int B, int H, int W, int C, int OH, int OW,
+                                           float* __restrict__ out) {
+  long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  long long total = static_cast<long long>(B) * OH * OW * C;
+  if (idx >= total) return;
+  int c = static_cast<int>(idx % C);
+  long long p = idx / C;
+  int ox = static_cast<int>(p % OW);
+  long long t = p / OW;
+  int oy = static_cast<int>(t % OH);
+  int b = static_cast<int>(t / OH);
+  int y0, y1, x0, x1; float fy, fx;
+  ac_coord(oy, H, OH, y0, y1, fy);
+  ac_coord(ox, W, OW, x0, x1, fx);
+  const float* base = in + static_cast<long long>(b) * H * W * C + c;
+  float v00 = base[(static_cast<long long>(y0) * W + x0) * C], v01 = base[(static_cast<long long>(y0) * W + x1) * C];
+  float v10 = base[(static_cast<long long>(y1) * W + x0) * C], v11 = base[(static_cast<long long>(y1) * W + x1) * C];
+  out[idx] = (1.f - fy) * ((1.f - fx) * v00 + fx * v01) + fy * ((1.f - fx) * v10 + fx * v11);
+}
+
+// torchvision roi_align bilinear tap with its edge rules (aligned=True, one sample per bin).
+__device__ __forceinline__ bool roi_coord(float c, int size, int& lo, int& hi, float& frac) {
+  if (c < -1.0f || c > static_cast<float>(size)) return false;
+  if (c <= 0.f) c = 0.f;
+  lo = static_cast<int>(c);
+  if (lo >= size - 1) { lo = hi = size - 1; c = static_cast<float>(lo); } else { hi = lo + 1; }
+  frac = c - lo;
+  return true;
+}
+
+template <bool F32>
+__global__ void roi_crop_zoom_kernel(const void* __restrict__ feat, int h, int w, int C, int in_ld,
+                                     const float* __restrict__ boxes, int T, float scale, void* __restrict__ out,
+                                     int out_ld, int out_col0) {
+  const int cg = F32 ? C : (C >> 3);
+  long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  long long total = static_cast<long long>(T) * h * w * cg;
+  if (idx >= total) return;
+  int g = static_cast<int>(idx % cg);
+  long long p = idx / cg;
+  int ox = static_cast<int>(p % w);
+  long long t2 = p / w;
+  int oy = static_cast<int>(t2 % h);
+  int t = static_cast<int>(t2 / h);
+  const float x1 = boxes[t * 4 + 0] * scale - 0.5f, y1 = boxes[t * 4 + 1] * scale - 0.5f;
+  const float x2 = boxes[t * 4 + 2] * scale - 0.5f, y2 = boxes[t * 4 + 3] * scale - 0.5f;
+  const float bw = (x2 - x1) / w, bh = (y2 - y1) / h;
+  const float sy = y1 + (oy + 0.5f) * bh, sx = x1 + (ox + 0.5f) * bw;
+  int yl, yh, xl, xh; float fy, fx;
+  bool ok = roi_coord(sy, h, yl, yh, fy);
+  ok = roi_coord(sx, w, xl, xh, fx) && ok;
+  if (F32) {
+    const float* f = static_cast<const float*>(feat) + g;
+    float v = 0.f;
+    if (ok) {
+      float v00 = f[(static_cast<long long>(yl) * w + xl) * in_ld], v01 = f[(static_cast<long long>(yl) * w + xh) * in_ld];
+      float v10 = f[(static_cast<long long>(yh) * w + xl) * in_ld], v11 = f[(static_cast<long long>(yh) * w + xh) * in_ld];
+      v = (1.f - fy) * (1.f - fx) * v00 + (1.f - fy) * fx * v01 + fy * (1.f - fx) * v10 + fy * fx * v11;
+    }
+    static_cast<float*>(out)[p * out_ld + out_col0 + g] = v;
+  } else {
+    float o[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) o[i] = 0.f;
+    if (ok) {
+      const bf16* f = static_cast<const bf16*>(feat) + g * 8;
+      float a[8], bb[8], c[8], d[8];
+      unpack8(*reinterpret_cast<const uint4*>(f + (static_cast<long long>(yl) * w + xl) * in_ld), a);
+      unpack8(*reinterpret_cast<const uint4*>(f + (static_cast<long long>(yl) * w + xh) * in_ld), bb);
+      unpack8(*reinterpret_cast<const uint4*>(f + (static_cast<long long>(yh) * w + xl) * in_ld), c);
+      unpack8(*reinterpret_cast<const uint4*>(f + (static_cast<long long>(yh) * w + xh) * in_ld), d);
+      const float w00 = (1.f - fy) * (1.f - fx), w01 = (1.f - fy) * fx, w10 = fy * (1.f - fx), w11 = fy * fx;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) o[i] = w00 * a[i] + w01 * bb[i] + w10 * c[i] + w11 * d[i];
+    }
+    *reinterpret_cast<uint4*>(static_cast<bf16*>(out) + p * out_ld + out_col0 + g * 8) = pack8(o);
+  }
+}
+
+__global__ void maxpool2_kernel(const bf16* __restrict__ in, int B, int H, int W, int C, int in_ld,
+                                bf16* __restrict__ out, int out_ld) {
+  const int OH = H / 2, OW = W / 2, cg = C >> 3;
+  long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  long long total = static_cast<long long>(B) * OH * OW * cg;
+  if (idx >= total) return;
+  int g = static_cast<int>(idx % cg);
+  long long p = idx / cg;
+  int ox = static_cast<int>(p % OW);
+  long long t = p / OW;
+  int oy = static_cast<int>(t % OH);
+  int b = static_cast<int>(t / OH);
+  const bf16* base = in + ((static_cast<long long>(b) * H + oy * 2) * W + ox * 2) * in_ld + g * 8;
+  float a[8], bb[8], c[8], d[8], o[8];
+  unpack8(*reinterpret_cast<const uint4*>(base), a);
+  unpack8(*reinterpret_cast<const uint4*>(base + in_ld), bb);
+  unpack8(*reinterpret_cast<const uint4*>(base + static_cast<long long>(W) * in_ld), c);
+  unpack8(*reinterpret_cast<const uint4*>(base + static_cast<long long>(W + 1) * in_ld), d);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) o[i] = fmaxf(fmaxf(a[i], bb[i]), fmaxf(c[i], d[i]));
+  *reinterpret_cast<uint4*>(out + p * out_ld + g * 8) = pack8(o);
+}
+
+__global__ void im2col_3x3_s2_kernel(const bf16* __restrict__ in, int B, int H, int W, int C, int in_ld,
+                                     bf16* __restrict__ out) {
+  const int OH = (H - 1) / 2 + 1, OW = (W - 1) / 2 + 1, cg = C >> 3;
+  long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  long long total = static_cast<long long>(B) * OH * OW * 9 * cg;
+  if (idx >= total) return;
+  int g = static_cast<int>(idx % cg);
+  long long t = idx / cg;
+  int tap = static_cast<int>(t % 9);
+  long long p = t / 9;
+  int ox = static_cast<int>(p % OW);
+  long long t2 = p / OW;
+  int oy = static_cast<int>(t2 % OH);
+  int b = static_cast<int>(t2 / OH);
+  int iy = oy * 2 - 1 + tap / 3, ix = ox * 2 - 1 + tap % 3;
+  uint4 v = make_uint4(0, 0, 0, 0);
+  if (iy >= 0 && iy < H && ix >= 0 && ix < W)
+    v = *reinterpret_cast<const uint4*>(in + ((static_cast<long long>(b) * H + iy) * W + ix) * in_ld + g * 8);
+  *reinterpret_cast<uint4*>(out + p * (9LL * C) + static_cast<long long>(tap) * C + g * 8) = v;
+}
+
+__global__ void crop_resize_kernel(const float* __restrict__ img, int H, int W, const int* __restrict__ origins, int T,
+                                   int th, int tw, int ph, int pw, float* __restrict__ out) {
+  long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  long long total = static_cast<long long>(T) * 3 * ph * pw;
+  if (idx >= total) return;
+  int ox = static_cast<int>(idx % pw);
+  long long t = idx / pw;
+  int oy = static_cast<int>(t % ph);
+  t /= ph;
+  int c = static_cast<int>(t % 3);
+  int ti = static_cast<int>(t / 3);
+  int y0, y1, x0, x1; float fy, fx;
+  ac_coord(oy, th, ph, y0, y1, fy);
+  ac_coord(ox, tw, pw, x0, x1, fx);
+  const float* base = img + (static_cast<long long>(c) * H + origins[ti * 2]) * W + origins[ti * 2 + 1];
+  float v00 = base[static_cast<long long>(y0) * W + x0], v01 = base[static_cast<long long>(y0) * W + x1];
+  float v10 = base[static_cast<long long>(y1) * W + x0], v11 = base[static_cast<long long>(y1) * W + x1];
+  out[idx] = (1.f - fy) * ((1.f - fx) * v00 + fx * v01) + fy * ((1.f - fx) * v10 + fx * v11);
+}
+
+__global__ void pack_unet_input_kernel(const float* __restrict__ cd, const float* __restrict__ fd,
+                                       const float* __restrict__ rgb, int T, int H, int W, bf16* __restrict__ out,
+                                       int ld) {
+  long long p = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  long long total = static_cast<long long>(T) * H * W;
+  if (p >= total) return;
+  long long hw = static_cast<long long>(H) * W;
+  int t = static_cast<int>(p / hw);
+  long long r = p - t * hw;
+  float f[8] = {cd[p], fd[p], rgb[(t * 3LL + 0) * hw + r], rgb[(t * 3LL + 1) * hw + r], rgb[(t * 3LL + 2) * hw + r],
+                0.f, 0.f, 0.f};
+  *reinterpret_cast<uint4*>(out + p * ld) = pack8(f);
+}
+
+// ------------------------------------------------------------------------------------------------ Swin / G2L
+__global__ void g2l_embed_kernel(const bf16* __restrict__ feat, int feat_ld, const float* __restrict__ ape, int n, int C,
+                                 float* __restrict__ x) {
+  long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (idx >= static_cast<long long>(n) * C) return;
+  int c = static_cast<int>(idx % C);
+  long long t = idx / C;
+  x[idx] = __bfloat162float(feat[t * feat_ld + c]) + ape[idx];
+}
+
+// One CTA per (window, head); thread i < 144 owns query row i.  K/V of the window live in shared memory as fp32.
+template <int HD>
+__global__ void __launch_bounds__(160) window_attention_kernel(const bf16* __restrict__ qkv,
+                                                               const float* __restrict__ bias_table, int Hp, int Wp,
+                                                               int C, int heads, int shift, bf16* __restrict__ out) {
+  constexpr int WS = 12, NT = 144;
+  __shared__ float sk[NT][HD + 1];
+  __shared__ float sv[NT][HD + 1];
+  __shared__ float sb[529];
+  __shared__ int stok[NT];
+  __shared__ int sreg[NT];
+  const int head = blockIdx.y;
+  const int win = blockIdx.x;
+  const int wpr = Wp / WS;
+  const int wy = win / wpr, wx = win - wy * wpr;
+  const int tid = threadIdx.x;
+  for (int i = tid; i < 529; i += blockDim.x) sb[i] = bias_table[i * heads + head];
+  if (tid < NT) {
+    int iy = tid / WS, ix = tid - iy * WS;
+    int ry = wy * WS + iy, rx = wx * WS + ix;                      // position in the rolled frame
+    int oy = (ry + shift) % Hp, ox = (rx + shift) % Wp;            // source position (torch.roll by -shift)
+    stok[tid] = oy * Wp + ox;
+    int hr = ry < Hp - WS ? 0 : (ry < Hp - shift ? 1 : 2);
+    int wr = rx < Wp - WS ? 0 : (rx < Wp - shift ? 1 : 2);
+    sreg[tid] = shift > 0 ? hr * 3 + wr : 0;
+  }
+  __syncthreads();
+  for (int i = tid; i < NT * HD; i += blockDim.x) {
+    int t = i / HD, d = i - t * HD;
+    const bf16* row = qkv + static_cast<long long>(stok[t]) * (3 * C) + head * HD + d;
+    sk[t][d] = __bfloat162float(row[C]);
+    sv[t][d] = __bfloat162float(row[2 * C]);
+  }
+  __syncthreads();
+  if (tid >= NT) return;
+  const float scale = rsqrtf(static_cast<float>(HD));
+  float q[HD];
+  {
+    const bf16* row = qkv + static_cast<long long>(stok[tid]) * (3 * C) + head * HD;
+#pragma unroll
+    for (int d = 0; d < HD; ++d) q[d] = __bfloat162float(row[d]) * scale;
+  }
+  const int iy = tid / WS, ix = tid - iy * WS, myreg = sreg[tid];
+  float m = -INFINITY, l = 0.f, acc[HD];
+#pragma unroll
+  for (int d = 0; d < HD; ++d) acc[d] = 0.f;
+  for (int j = 0; j < NT; ++j) {
+    float s = 0.f;
+#pragma unroll
+    for (int d = 0; d < HD; ++d) s += q[d] * sk[j][d];
+    int jy = j / WS, jx = j - jy * WS;
+    s += sb[(iy - jy + WS - 1) * (2 * WS - 1) + (ix - jx + WS - 1)];
+    if (sreg[j] != myreg) s += -100.0f;
+    float mn = fmaxf(m, s);
+    float a = __expf(m - mn), p = __expf(s - mn);
+    l = l * a + p;
+#pragma unroll
+    for (int d = 0; d < HD; ++d) acc[d] = acc[d] * a + p * sv[j][d];
+    m = mn;
+  }
+  const float inv = 1.f / l;
+  bf16* orow = out + static_cast<long long>(stok[tid]) * C + head * HD;
+#pragma unroll
+  for (int d = 0; d < HD; ++d) orow[d] = __float2bfloat16(acc[d] * inv);
+}
+
+__global__ void swin_residual_crop_kernel(float* __restrict__ x, const float* __restrict__ y, int H, int W, int Wp, int C) {
+  long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (idx >= static_cast<long long>(H) * W * C) return;
+  int c = static_cast<int>(idx % C);
+  long long t = idx / C;
+  int xx = static_cast<int>(t % W), yy = static_cast<int>(t / W);
+  x[idx] += y[(static_cast<long long>(yy) * Wp + xx) * C + c];
+}
+
+// ------------------------------------------------------------------------------------------------ metric-bins tail
+__global__ void add_upsampled_kernel(const bf16* __restrict__ a, int B, int H, int W, int C, const bf16* __restrict__ prev,
+                                     int PH, int PW, bf16* __restrict__ out) {
+  const int cg = C >> 3;
+  long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  long long total = static_cast<long long>(B) * H * W * cg;
+  if (idx >= total) return;
+  int g = static_cast<int>(idx % cg);
+  long long p = idx / cg;
+  int ox = static_cast<int>(p % W);
+  long long t = p / W;
+  int oy = static_cast<int>(t % H);
+  int b = static_cast<int>(t / H);
+  int y0, y1, x0, x1; float fy, fx;
+  ac_coord(oy, PH, H, y0, y1, fy);
+  ac_coord(ox, PW, W, x0, x1, fx);
+  const bf16* base = prev + static_cast<long long>(b) * PH * PW * C + g * 8;
+  float q0[8], q1[8], q2[8], q3[8], s[8], o[8];
+  unpack8(*reinterpret_cast<const uint4*>(base + (static_cast<long long>(y0) * PW + x0) * C), q0);
+  unpack8(*reinterpret_cast<const uint4*>(base + (static_cast<long long>(y0) * PW + x1) * C), q1);
+  unpack8(*reinterpret_cast<const uint4*>(base + (static_cast<long long>(y1) * PW + x0) * C), q2);
+  unpack8(*reinterpret_cast<const uint4*>(base + (static_cast<long long>(y1) * PW + x1) * C), q3);
+  unpack8(*reinterpret_cast<const uint4*>(a + p * C + g * 8), s);
+  const float w00 = (1.f - fy) * (1.f - fx), w01 = (1.f - fy) * fx, w10 = fy * (1.f - fx), w11 = fy * fx;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) o[i] = s[i] + w00 * q0[i] + w01 * q1[i] + w10 * q2[i] + w11 * q3[i];
+  *reinterpret_cast<uint4*>(out + p * C + g * 8) = pack8(o);
+}
+
+// one thread per (pixel, bin): b = up(b_prev); b += mean_a( dx / (1 + 300 dx^2) ), dx = A_a - b.
+__global__ void attractor_kernel(const float* __restrict__ A, int A_ld, int nA, const float* __restrict__ b_prev, int PH,
+                                 int PW, int B, int H, int W, int nbins, int kind_mean, float* __restrict__ b_out) {
+  long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  long long total = static_cast<long long>(B) * H * W * nbins;
+  if (idx >= total) return;
+  int k = static_cast<int>(idx % nbins);
+  long long p = idx / nbins;
+  int ox = static_cast<int>(p % W);
+  long long t = p / W;
+  int oy = static_cast<int>(t % H);
+  int b = static_cast<int>(t / H);
+  int y0, y1, x0, x1; float fy, fx;
+  ac_coord(oy, PH, H, y0, y1, fy);
+  ac_coord(ox, PW, W, x0, x1, fx);
+  const float* base = b_prev + static_cast<long long>(b) * PH * PW * nbins + k;
+  float v00 = base[(static_cast<long long>(y0) * PW + x0) * nbins], v01 = base[(static_cast<long long>(y0) * PW + x1) * nbins];
+  float v10 = base[(static_cast<long long>(y1) * PW + x0) * nbins], v11 = base[(static_cast<long long>(y1) * PW + x1) * nbins];
+  float bc = (1.f - fy) * ((1.f - fx) * v00 + fx * v01) + fy * ((1.f - fx) * v10 + fx * v11);
+  const float* Ap = A + p * A_ld;
+  float s = 0.f;
+  for (int a = 0; a < nA; ++a) {
+    float dx = Ap[a] - bc;
+    s += dx / (1.f + 300.f * dx * dx);
+  }
+  if (kind_mean) s /= nA;
+  b_out[idx] = bc + s;
+}
+
+// one warp per pixel, 2 bins per lane (nbins == 64).
+__global__ void logbinom_depth_kernel(const float* __restrict__ pt, int pt_ld, const float* __restrict__ bc, int BH, int BW,
+                                      int B, int H, int W, int nbins, float min_t, float max_t, float* __restrict__ depth) {
+  long long p = blockIdx.x * static_cast<long long>(blockDim.x >> 5) + (threadIdx.x >> 5);
+  int lane = threadIdx.x & 31;
+  long long total = static_cast<long long>(B) * H * W;
+  if (p >= total) return;
+  int ox = static_cast<int>(p % W);
+  long long t = p / W;
+  int oy = static_cast<int>(t % H);
+  int b = static_cast<int>(t / H);
+  const float* q = pt + p * pt_ld;
+  float p0 = q[0] + 1e-4f, p1 = q[1] + 1e-4f, t0 = q[2] + 1e-4f, t1 = q[3] + 1e-4f;
+  float pr = p0 / (p0 + p1);
+  float tt = t0 / (t0 + t1);
+  tt = (max_t - min_t) * tt + min_t;
+  float om = fminf(fmaxf(1.f - pr, 1e-4f), 1.f);
+  pr = fminf(fmaxf(pr, 1e-4f), 1.f);
+  const float lp = logf(pr), lq = logf(om);
+  int y0, y1, x0, x1; float fy, fx;
+  ac_coord(oy, BH, H, y0, y1, fy);
+  ac_coord(ox, BW, W, x0, x1, fx);
+  const float* base = bc + static_cast<long long>(b) * BH * BW * nbins;
+  const float Km1 = static_cast<float>(nbins - 1);
+  float yv[2], cv[2];
+  float mx = -INFINITY;
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    int k = lane + 32 * i;
+    float kf = static_cast<float>(k);
+    float n_ = Km1 + 1e-7f, k_ = kf + 1e-7f;
+    float logc = n_ * logf(n_) - k_ * logf(k_) - (n_ - k_) * logf(n_ - k_ + 1e-7f);
+    yv[i] = (logc + kf * lp + (Km1 - kf) * lq) / tt;
+    mx = fmaxf(mx, yv[i]);
+    float v00 = base[(static_cast<long long>(y0) * BW + x0) * nbins + k], v01 = base[(static_cast<long long>(y0) * BW + x1) * nbins + k];
+    float v10 = base[(static_cast<long long>(y1) * BW + x0) * nbins + k], v11 = base[(static_cast<long long>(y1) * BW + x1) * nbins + k];
+    cv[i] = (1.f - fy) * ((1.f - fx) * v00 + fx * v01) + fy * ((1.f - fx) * v10 + fx * v11);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  float e0 = expf(yv[0] - mx), e1 = expf(yv[1] - mx);
+  float den = warp_sum(e0 + e1);
+  float num = warp_sum(e0 * cv[0] + e1 * cv[1]);
+  if (lane == 0) depth[p] = num / den;
+}
+
+// ------------------------------------------------------------------------------------------------ stitch
+__global__ void stitch_accumulate_kernel(float* __restrict__ num, float* __restrict__ den, int CH, int CW,
+                                         const float* __restrict__ tiles, int T, int th, int tw,
+                                         const int* __restrict__ origins, const float* __restrict__ mask, int uh, int uw) {
+  const int oh = uh > 0 ? uh : th, ow = uw > 0 ? uw : tw;
+  long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  long long total = static_cast<long long>(T) * oh * ow;
+  if (idx >= total) return;
+  int x = static_cast<int>(idx % ow);
+  long long t2 = idx / ow;
+  int y = static_cast<int>(t2 % oh);
+  int t = static_cast<int>(t2 / oh);
+  int sy = y, sx = x;
+  if (uh > 0) {   // F.interpolate default 'nearest': src = floor(dst * in/out)
+    sy = min(static_cast<int>(floorf(y * (static_cast<float>(th) / uh))), th - 1);
+    sx = min(static_cast<int>(floorf(x * (static_cast<float>(tw) / uw))), tw - 1);
+  }
+  float d = tiles[(static_cast<long long>(t) * th + sy) * tw + sx];
+  float m = mask[static_cast<long long>(y) * ow + x];
+  int cy = origins[t * 2] + y, cx = origins[t * 2 + 1] + x;
+  if (cy < CH && cx < CW) {
+    long long o = static_cast<long long>(cy) * CW + cx;
+    atomicAdd(num + o, m * d);
+    atomicAdd(den + o, m);
+  }
+}
+
+__global__ void stitch_finalize_kernel(const float* __restrict__ num, const float* __restrict__ den, long long n,
+                                       float* __restrict__ out) {
+  long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (i < n) out[i] = num[i] / den[i];
+}
+
+__global__ void stitch_resize_kernel(const float* __restrict__ num, const float* __restrict__ den, int H, int W, int OH,
+                                     int OW, float* __restrict__ num_out, float* __restrict__ den_out) {
+  long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (idx >= static_cast<long long>(OH) * OW) return;
+  int ox = static_cast<int>(idx % OW), oy = static_cast<int>(idx / OW);
+  int sy = min(static_cast<int>(floorf(oy * (static_cast<float>(H) / OH))), H - 1);
+  int sx = min(static_cast<int>(floorf(ox * (static_cast<float>(W) / OW))), W - 1);
+  long long s = static_cast<long long>(sy) * W + sx;
+  float avg = num[s] / den[s];
+  int y0, y1, x0, x1; float fy, fx;
+  ac_coord(oy, H, OH, y0, y1, fy);
+  ac_coord(ox, W, OW, x0, x1, fx);
+  float c = (1.f - fy) * ((1.f - fx) * den[static_cast<long long>(y0) * W + x0] + fx * den[static_cast<long long>(y0) * W + x1]) +
+            fy * ((1.f - fx) * den[static_cast<long long>(y1) * W + x0] + fx * den[static_cast<long long>(y1) * W + x1]);
+  num_out[idx] = avg * c;
+  den_out[idx] = c;
+}
+
+}  // namespace pf
+
+using namespace pf;
+#define ST static_cast<cudaStream_t>(stream)
+
+extern "C" {
+
+int pf_layernorm(const float* x, int32_t x_ld, const float* w, const float* b, float eps, int32_t rows, int32_t C,
+                 void* out, int32_t out_ld, void* stream) {
+  if (C % 4 || x_ld % 4 || out_ld % 4) return set_error("pf_layernorm: C and strides must be multiples of 4");
+  layernorm_kernel<<<nblocks(rows, 8), 256, 0, ST>>>(x, x_ld, w, b, eps, rows, C, static_cast<bf16*>(out), out_ld);
+  return check_launch("layernorm_kernel");
+}
+
+int pf_patch_im2col(const float* img, int32_t B, int32_t H, int32_t W, void* out, int32_t ld, void* stream) {
+  if (H % 14 || W % 14 || ld < 588) return set_error("pf_patch_im2col: image must be a multiple of 14, ld >= 588");
+  long long total = static_cast<long long>(B) * (H / 14) * (W / 14) * ld;
+  patch_im2col_kernel<<<nblocks(total, 256), 256, 0, ST>>>(img, B, H, W, static_cast<bf16*>(out), ld);
+  return check_launch("patch_im2col_kernel");
+}
+
+int pf_assemble_tokens(const float* patch, const float* cls, const float* pos, int32_t B, int32_t n_patch, int32_t D,
+                       float* tokens, void* stream) {
+  long long total = static_cast<long long>(B) * (n_patch + 1) * D;
+  assemble_tokens_kernel<<<nblocks(total, 256), 256, 0, ST>>>(patch, cls, pos, B, n_patch, D, tokens);
+  return check_launch("assemble_tokens_kernel");
+}
+
+int pf_f32_to_bf16(const float* in, int64_t n, void* out, void* stream) {
+  f32_to_bf16_kernel<<<nblocks(n, 256), 256, 0, ST>>>(in, n, static_cast<bf16*>(out));
+  return check_launch("f32_to_bf16_kernel");
+}
+
+int pf_resize_bilinear(const void* in, int32_t B, int32_t H, int32_t W, int32_t C, int32_t in_ld, int32_t OH,
+                       int32_t OW, void* out, int32_t out_ld, int32_t out_col0, void* stream) {
+  if (C % 8 || in_ld % 8 || out_ld % 8 || out_col0 % 8) return set_error("pf_resize_bilinear: channel counts/strides must be multiples of 8");
+  long long total = static_cast<long long>(B) * OH * OW * (C / 8);
+  resize_bilinear_kernel<<<nblocks(total, 256), 256, 0, ST>>>(static_cast<const bf16*>(in), B, H, W, C, in_ld, OH, OW,
+                                                               static_cast<bf16*>(out), out_ld, out_col0);
+  return check_launch("resize_bilinear_kernel");
+}
+
+int pf_resize_bilinear_f32(const float* in, int32_t B, int32_t H, int32_t W, int32_t C, int32_t OH, int32_t OW,
+                           float* out, void* stream) {
+  long long total = static_cast<long long>(B) * OH * OW * C;
+  resize_bilinear_f32_kernel<<<nblocks(total, 256), 256, 0, ST>>>(in, B, H, W, C, OH, OW, out);
+  return check_launch("resize_bilinear_f32_kernel");
+}
+
+int pf_roi_crop_zoom(const void* feat, int32_t in_f32, int32_t h, int32_t w, int32_t C, int32_t in_ld,
+                     const float* boxes, int32_t T, float spatial_scale, void* out, int32_t out_ld, int32_t out_col0,
+                     void* stream) {
+  if (in_f32) {
+    long long total = static_cast<long long>(T) * h * w * C;
+    roi_crop_zoom_kernel<true><<<nblocks(total, 256), 256, 0, ST>>>(feat, h, w, C, in_ld, boxes, T, spatial_scale, out,
+                                                                    out_ld, out_col0);
+  } else {
+    if (C % 8 || in_ld % 8 || out_ld % 8 || out_col0 % 8) return set_error("pf_roi_crop_zoom: channels/strides must be multiples of 8");
+    long long total = static_cast<long long>(T) * h * w * (C / 8);
+    roi_crop_zoom_kernel<false><<<nblocks(total, 256), 256, 0, ST>>>(feat, h, w, C, in_ld, boxes, T, spatial_scale, out,
+                                                                     out_ld, out_col0);
+  }
+  return check_launch("roi_crop_zoom_kernel");
+}
+
+int pf_maxpool2(const void* in, int32_t B, int32_t H, int32_t W, int32_t C, int32_t in_ld, void* out, int32_t out_ld,
+                void* stream) {
+  if (C % 8 || in_ld % 8 || out_ld % 8) return set_error("pf_maxpool2: channels/strides must be multiples of 8");
+  long long total = static_cast<long long>(B) * (H / 2) * (W / 2) * (C / 8);
+  maxpool2_kernel<<<nblocks(total, 256), 256, 0, ST>>>(static_cast<const bf16*>(in), B, H, W, C, in_ld,
+                                                        static_cast<bf16*>(out), out_ld);
+  return check_launch("maxpool2_kernel");
+}
+
+int pf_im2col_3x3_s2(const void* in, int32_t B, int32_t H, int32_t W, int32_t C, int32_t in_ld, void* out,
+                     void* stream) {
+  if (C % 8 || in_ld % 8) return set_error("pf_im2col_3x3_s2: channels/strides must be multiples of 8");
+  long long total = static_cast<long long>(B) * ((H - 1) / 2 + 1) * ((W - 1) / 2 + 1) * 9 * (C / 8);
+  im2col_3x3_s2_kernel<<<nblocks(total, 256), 256, 0, ST>>>(static_cast<const bf16*>(in), B, H, W, C, in_ld,
+                                                             static_cast<bf16*>(out));
+  return check_launch("im2col_3x3_s2_kernel");
+}
+
+int pf_crop_resize(const float* img, int32_t H, int32_t W, const int32_t* origins, int32_t T, int32_t th, int32_t tw,
+                   int32_t ph, int32_t pw, float* out_planar, void* stream) {
+  long long total = static_cast<long long>(T) * 3 * ph * pw;
+  crop_resize_kernel<<<nblocks(total, 256), 256, 0, ST>>>(img, H, W, origins, T, th, tw, ph, pw, out_planar);
+  return check_launch("crop_resize_kernel");
+}
+
+int pf_pack_unet_input(const float* coarse_depth_roi, const float* fine_depth, const float* rgb_planar, int32_t T,
+                       int32_t H, int32_t W, void* out, int32_t ld, void* stream) {
+  if (ld % 8) return set_error("pf_pack_unet_input: ld must be a multiple of 8");
+  long long total = static_cast<long long>(T) * H * W;
+  pack_unet_input_kernel<<<nblocks(total, 256), 256, 0, ST>>>(coarse_depth_roi, fine_depth, rgb_planar, T, H, W,
+                                                               static_cast<bf16*>(out), ld);
+  return check_launch("pack_unet_input_kernel");
+}
+
+int pf_g2l_embed(const void* feat, int32_t feat_ld, const float* ape, int32_t n, int32_t C, float* x, void* stream) {
+  g2l_embed_kernel<<<nblocks(static_cast<long long>(n) * C, 256), 256, 0, ST>>>(static_cast<const bf16*>(feat), feat_ld,
+                                                                                 ape, n, C, x);
+  return check_launch("g2l_embed_kernel");
+}
+
+int pf_swin_norm_pad(const float* x, const float* w, const float* b, float eps, int32_t H, int32_t W, int32_t Hp,
+                     int32_t Wp, int32_t C, void* out, void* stream) {
+  if (C % 4) return set_error("pf_swin_norm_pad: C must be a multiple of 4");
+  swin_norm_pad_kernel<<<nblocks(static_cast<long long>(Hp) * Wp, 8), 256, 0, ST>>>(x, w, b, eps, H, W, Hp, Wp, C,
+                                                                                     static_cast<bf16*>(out));
+  return check_launch("swin_norm_pad_kernel");
+}
+
+int pf_window_attention(const void* qkv, const float* bias_table, int32_t Hp, int32_t Wp, int32_t C, int32_t heads,
+                        int32_t shift, void* out, void* stream) {
+  if (Hp % 12 || Wp % 12) return set_error("pf_window_attention: padded grid must be a multiple of the 12x12 window");
+  dim3 grid((Hp / 12) * (Wp / 12), heads);
+  const bf16* q = static_cast<const bf16*>(qkv);
+  bf16* o = static_cast<bf16*>(out);
+  switch (C / heads) {
+    case 2: window_attention_kernel<2><<<grid, 160, 0, ST>>>(q, bias_table, Hp, Wp, C, heads, shift, o); break;
+    case 4: window_attention_kernel<4><<<grid, 160, 0, ST>>>(q, bias_table, Hp, Wp, C, heads, shift, o); break;
+    case 8: window_attention_kernel<8><<<grid, 160, 0, ST>>>(q, bias_table, Hp, Wp, C, heads, shift, o); break;
+    case 16: window_attention_kernel<16><<<grid, 160, 0, ST>>>(q, bias_table, Hp, Wp, C, heads, shift, o); break;
+    case 32: window_attention_kernel<32><<<grid, 160, 0, ST>>>(q, bias_table, Hp, Wp, C, heads, shift, o); break;
+    default: return set_error("pf_window_attention: unsupported head_dim %d", C / heads);
+  }
+  return check_launch("window_attention_kernel");
+}
+
+int pf_swin_residual_crop(float* x, const float* y, int32_t H, int32_t W, int32_t Wp, int32_t C, void* stream) {
+  swin_residual_crop_kernel<<<nblocks(static_cast<long long>(H) * W * C, 256), 256, 0, ST>>>(x, y, H, W, Wp, C);
+  return check_launch("swin_residual_crop_kernel");
+}
+
+int pf_add_upsampled(const void* a, int32_t B, int32_t H, int32_t W, int32_t C, const void* prev, int32_t PH, int32_t PW,
+                     void* out, void* stream) {
+  if (C % 8) return set_error("pf_add_upsampled: C must be a multiple of 8");
+  long long total = static_cast<long long>(B) * H * W * (C / 8);
+  add_upsampled_kernel<<<nblocks(total, 256), 256, 0, ST>>>(static_cast<const bf16*>(a), B, H, W, C,
+                                                             static_cast<const bf16*>(prev), PH, PW, static_cast<bf16*>(out));
+  return check_launch("add_upsampled_kernel");
+}
+
+int pf_attractor(const float* A, int32_t A_ld, int32_t nA, const float* b_prev, int32_t PH, int32_t PW, int32_t B,
+                 int32_t H, int32_t W, int32_t nbins, int32_t kind_mean, float* b_out, void* stream) {
+  long long total = static_cast<long long>(B) * H * W * nbins;
+  attractor_kernel<<<nblocks(total, 256), 256, 0, ST>>>(A, A_ld, nA, b_prev, PH, PW, B, H, W, nbins, kind_mean, b_out);
+  return check_launch("attractor_kernel");
+}
+
+int pf_logbinom_depth(const float* pt, int32_t pt_ld, const float* b_centers, int32_t BH, int32_t BW, int32_t B,
+                      int32_t H, int32_t W, int32_t nbins, float min_temp, float max_temp, float* depth, void* stream) {
+  if (nbins != 64) return set_error("pf_logbinom_depth: n_bins must be 64");
+  long long total = static_cast<long long>(B) * H * W;
+  logbinom_depth_kernel<<<nblocks(total, 8), 256, 0, ST>>>(pt, pt_ld, b_centers, BH, BW, B, H, W, nbins, min_temp,
+                                                            max_temp, depth);
+  return check_launch("logbinom_depth_kernel");
+}
+
+int pf_stitch_accumulate(float* num, float* den, int32_t CH, int32_t CW, const float* tiles, int32_t T, int32_t th,
+                         int32_t tw, const int32_t* origins, const float* mask, int32_t up_h, int32_t up_w,
+                         void* stream) {
+  long long total = static_cast<long long>(T) * (up_h > 0 ? up_h : th) * (up_w > 0 ? up_w : tw);
+  stitch_accumulate_kernel<<<nblocks(total, 256), 256, 0, ST>>>(num, den, CH, CW, tiles, T, th, tw, origins, mask, up_h,
+                                                                 up_w);
+  return check_launch("stitch_accumulate_kernel");
+}
+
+int pf_stitch_finalize(const float* num, const float* den, int64_t n, float* out, void* stream) {
+  stitch_finalize_kernel<<<nblocks(n, 256), 256, 0, ST>>>(num, den, n, out);
+  return check_launch("stitch_finalize_kernel");
+}
+
+int pf_stitch_resize(const float* num, const float* den, int32_t H, int32_t W, int32_t OH, int32_t OW, float* num_out,
+                     float* den_out, void* stream) {
+  stitch_resize_kernel<<<nblocks(static_cast<long long>(OH) * OW, 256), 256, 0, ST>>>(num, den, H, W, OH, OW, num_out,
+                                                                                       den_out);
+  return check_launch("stitch_resize_kernel");
+}
+
+}  // extern "C"

@@ -173,8 +173,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1) pf_gemm_kernel(const __grid_c
       int ocol0 = c.n0;     // output column of accumulator column 0
       if (d.ps > 1 && d.a_mode == 0) {
         // ConvTranspose k==s: columns are ordered (ky, kx, cout); this N tile belongs to one (ky,kx).
-        int tap = c.n0 / d.ps_cout;
-        ocol0 = c.n0 - tap * d.ps_cout;
+        int tap = c.n0 / d.ps_cout_pad;
+        ocol0 = c.n0 - tap * d.ps_cout_pad;
         int ky = tap / d.ps, kx = tap - ky * d.ps;
         int m = c.m0 + r;
         int img = m / (d.H * d.W);
@@ -190,73 +190,88 @@ __global__ void __launch_bounds__(kGemmThreads, 1) pf_gemm_kernel(const __grid_c
         tmem_ld32(taddr + cb, v);
         tmem_ld_wait();
         if (row_ok) {
-          const int ncol = c.n0 + cb;            // accumulator/global N index of v[0]
-          const int oc = ocol0 + cb + d.out_col0;
-          float f[32];
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            float x = __uint_as_float(v[j]);
-            if (d.bias != nullptr && ncol + j < d.N) x += __ldg(d.bias + ncol + j);
-            f[j] = apply_act(x, d.act);
-          }
-          if (d.res1 != nullptr) {
-            const __nv_bfloat16* rp = d.res1 + orow * d.res_ld + (ocol0 + cb);
-#pragma unroll
-            for (int j = 0; j < 32; ++j) if (ncol + j < d.N) f[j] += __bfloat162float(rp[j]);
-          }
-          if (d.res2 != nullptr) {
-            const __nv_bfloat16* rp = d.res2 + orow * d.res_ld + (ocol0 + cb);
-#pragma unroll
-            for (int j = 0; j < 32; ++j) if (ncol + j < d.N) f[j] += __bfloat162float(rp[j]);
-          }
-          if (d.vt != nullptr && ncol >= d.vt_col0) {
-            // attention V written transposed: vt[(b*heads + h)*64 + dd][token]
-            int m = static_cast<int>(orow);
-            int b = m / d.vt_seq, tok = m - b * d.vt_seq;
+          const int ncol = c.n0 + cb;            // global N index of v[0] (selects the V^T path)
+          const int lcol = ocol0 + cb;           // logical output channel of v[0] (bias / gamma / residual index)
+          const int oc = lcol + d.out_col0;      // physical output column
+          const int nvalid = min(32, d.n_logical - lcol);   // columns of this chunk that exist
+          if (nvalid > 0) {
+            float f[32];
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
-              int cc = ncol + j - d.vt_col0;      // h*64 + dd
-              if (ncol + j < d.N)
-                d.vt[(static_cast<long long>(b) * d.vt_dim + cc) * d.vt_seq_pad + tok] = __float2bfloat16(f[j]);
+              float x = __uint_as_float(v[j]);
+              if (d.bias != nullptr && j < nvalid) x += __ldg(d.bias + lcol + j);
+              f[j] = apply_act(x, d.act);
             }
-          } else if (d.gamma != nullptr) {
-            // x <- x + gamma * (acc + bias): fp32 residual stream updated in place
-            float* xp = reinterpret_cast<float*>(d.out) + orow * d.out_ld + oc;
-            if (ncol + 32 <= d.N) {
+            if (d.res1 != nullptr) {
+              const __nv_bfloat16* rp = d.res1 + orow * d.res_ld + lcol;
 #pragma unroll
-              for (int j = 0; j < 32; j += 4) {
-                float4 xv = *reinterpret_cast<float4*>(xp + j);
-                float4 g = __ldg(reinterpret_cast<const float4*>(d.gamma + ncol + j));
-                xv.x += g.x * f[j]; xv.y += g.y * f[j + 1]; xv.z += g.z * f[j + 2]; xv.w += g.w * f[j + 3];
-                *reinterpret_cast<float4*>(xp + j) = xv;
+              for (int j = 0; j < 32; ++j) if (j < nvalid) f[j] += __bfloat162float(rp[j]);
+            }
+            if (d.res2 != nullptr) {
+              const __nv_bfloat16* rp = d.res2 + orow * d.res_ld + lcol;
+#pragma unroll
+              for (int j = 0; j < 32; ++j) if (j < nvalid) f[j] += __bfloat162float(rp[j]);
+            }
+            if (d.vt != nullptr && ncol >= d.vt_col0) {
+              // attention V written transposed: vt[(b*heads + h)*64 + dd][token]
+              int m = static_cast<int>(orow);
+              int b = m / d.vt_seq, tok = m - b * d.vt_seq;
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                int cc = ncol + j - d.vt_col0;      // h*64 + dd
+                if (j < nvalid)
+                  d.vt[(static_cast<long long>(b) * d.vt_dim + cc) * d.vt_seq_pad + tok] = __float2bfloat16(f[j]);
+              }
+            } else if (d.gamma != nullptr) {
+              // x <- x + gamma * (acc + bias): fp32 residual stream updated in place
+              float* xp = reinterpret_cast<float*>(d.out) + orow * d.out_ld + oc;
+              if (nvalid == 32) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                  float4 xv = *reinterpret_cast<float4*>(xp + j);
+                  float4 g = __ldg(reinterpret_cast<const float4*>(d.gamma + lcol + j));
+                  xv.x += g.x * f[j]; xv.y += g.y * f[j + 1]; xv.z += g.z * f[j + 2]; xv.w += g.w * f[j + 3];
+                  *reinterpret_cast<float4*>(xp + j) = xv;
+                }
+              } else {
+                for (int j = 0; j < nvalid; ++j) xp[j] += __ldg(d.gamma + lcol + j) * f[j];
+              }
+            } else if (d.out_f32) {
+              float* op = reinterpret_cast<float*>(d.out) + orow * d.out_ld + oc;
+              if (nvalid == 32) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 4)
+                  *reinterpret_cast<float4*>(op + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+              } else {
+                for (int j = 0; j < nvalid; ++j) op[j] = f[j];
               }
             } else {
-              for (int j = 0; j < 32; ++j) if (ncol + j < d.N) xp[j] += __ldg(d.gamma + ncol + j) * f[j];
-            }
-          } else if (d.out_f32) {
-            float* op = reinterpret_cast<float*>(d.out) + orow * d.out_ld + oc;
-            if (ncol + 32 <= d.N) {
+              __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(d.out) + orow * d.out_ld + oc;
+              if (nvalid == 32) {
 #pragma unroll
-              for (int j = 0; j < 32; j += 4)
-                *reinterpret_cast<float4*>(op + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
-            } else {
-              for (int j = 0; j < 32; ++j) if (ncol + j < d.N) op[j] = f[j];
-            }
-          } else {
-            __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(d.out) + orow * d.out_ld + oc;
-            if (ncol + 32 <= d.N) {
-#pragma unroll
-              for (int j = 0; j < 32; j += 8) {
-                uint4 pk = make_uint4(pack_bf16(f[j], f[j + 1]), pack_bf16(f[j + 2], f[j + 3]),
-                                      pack_bf16(f[j + 4], f[j + 5]), pack_bf16(f[j + 6], f[j + 7]));
-                *reinterpret_cast<uint4*>(op + j) = pk;
+                for (int j = 0; j < 32; j += 8) {
+                  uint4 pk = make_uint4(pack_bf16(f[j], f[j + 1]), pack_bf16(f[j + 2], f[j + 3]),
+                                        pack_bf16(f[j + 4], f[j + 5]), pack_bf16(f[j + 6], f[j + 7]));
+                  *reinterpret_cast<uint4*>(op + j) = pk;
+                }
+              } else {
+                for (int j = 0; j < nvalid; ++j) op[j] = __float2bfloat16(f[j]);
               }
-            } else {
-              for (int j = 0; j < 32; ++j) if (ncol + j < d.N) op[j] = __float2bfloat16(f[j]);
-            }
-            if (d.out2 != nullptr) {
-              __nv_bfloat16* o2 = d.out2 + orow * d.out2_ld + (ocol0 + cb);
-              for (int j = 0; j < 32; ++j) if (ncol + j < d.N) o2[j] = __float2bfloat16(fmaxf(f[j], 0.0f));
+              if (d.out2 != nullptr) {
+                __nv_bfloat16* o2 = d.out2 + orow * d.out2_ld + lcol;
+                if (nvalid == 32) {
+#pragma unroll
+                  for (int j = 0; j < 32; j += 8) {
+                    uint4 pk = make_uint4(pack_bf16(fmaxf(f[j], 0.f), fmaxf(f[j + 1], 0.f)),
+                                          pack_bf16(fmaxf(f[j + 2], 0.f), fmaxf(f[j + 3], 0.f)),
+                                          pack_bf16(fmaxf(f[j + 4], 0.f), fmaxf(f[j + 5], 0.f)),
+                                          pack_bf16(fmaxf(f[j + 6], 0.f), fmaxf(f[j + 7], 0.f)));
+                    *reinterpret_cast<uint4*>(o2 + j) = pk;
+                  }
+                } else {
+                  for (int j = 0; j < nvalid; ++j) o2[j] = __float2bfloat16(fmaxf(f[j], 0.0f));
+                }
+              }
             }
           }
         }

@@ -23,7 +23,8 @@ struct GemmDesc {
   int out_f32, out_ld, out_col0;
   __nv_bfloat16* out2;
   int out2_ld;
-  int ps, ps_cout;
+  int ps, ps_cout_pad;   // pixel shuffle factor, per-tap column stride of the packed weight
+  int n_logical;         // logical output channels (N, or Cout for pixel shuffle)
   __nv_bfloat16* vt;
   int vt_col0, vt_seq, vt_seq_pad, vt_dim;
 };

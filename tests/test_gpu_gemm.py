@@ -1,0 +1,144 @@
+"""pf_gemm (tcgen05 implicit GEMM) vs torch fp32 on the same bf16-rounded operands."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from gpu_util import bf, check, from_nhwc, rb, to_nhwc
+
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(300)]
+
+
+def _ops():
+    from patchfusion_b200 import ops
+    return ops
+
+
+@pytest.mark.parametrize('M,K,N,act', [(300, 192, 96, 'gelu'), (128, 64, 32, 'none'), (2074, 1024, 3072, 'none'),
+                                       (1036, 592, 384, 'relu'), (777, 384, 1536, 'softplus'), (4144, 256, 544, 'none')])
+def test_linear(cuda, M, K, N, act):
+    ops = _ops()
+    g = torch.Generator(device='cuda').manual_seed(M + K + N)
+    x = torch.randn(M, K, device=cuda, generator=g)
+    w = torch.randn(N, K, device=cuda, generator=g) / K ** 0.5
+    b = torch.randn(N, device=cuda, generator=g)
+    pw = ops.pack_weight(w, b)
+    ld = ops.pad_to(K, 8)
+    xa = torch.zeros(M, ld, dtype=torch.bfloat16, device=cuda)
+    xa[:, :K] = bf(x)
+    out = torch.full((M, ops.pad_to(N, 8)), 7.0, dtype=torch.bfloat16, device=cuda)
+    acts = dict(none=ops.ACT_NONE, relu=ops.ACT_RELU, gelu=ops.ACT_GELU, softplus=ops.ACT_SOFTPLUS)
+    ops.gemm(pw, [xa], out, act=acts[act])
+    torch.cuda.synchronize()
+    ref = F.linear(rb(x), rb(w), b)
+    ref = dict(none=lambda t: t, relu=F.relu, gelu=F.gelu, softplus=F.softplus)[act](ref)
+    check('linear %dx%dx%d %s' % (M, K, N, act), out[:, :N], ref, 1e-2)
+    if out.shape[1] > N:
+        assert (out[:, N:] == 7.0).all(), 'columns beyond N were written'
+
+
+def test_linear_f32_and_layerscale(cuda):
+    ops = _ops()
+    g = torch.Generator(device='cuda').manual_seed(1)
+    M, K, N = 1037, 1536, 384
+    x = torch.randn(M, K, device=cuda, generator=g)
+    w = torch.randn(N, K, device=cuda, generator=g) / K ** 0.5
+    b = torch.randn(N, device=cuda, generator=g)
+    gamma = torch.rand(N, device=cuda, generator=g)
+    res = torch.randn(M, N, device=cuda, generator=g)
+    pw = ops.pack_weight(w, b)
+    out = torch.zeros(M, N, dtype=torch.float32, device=cuda)
+    ops.gemm(pw, [bf(x).contiguous()], out)
+    ref = F.linear(rb(x), rb(w), b)
+    check('linear fp32 out', out, ref, 2e-5)
+    xres = res.clone()
+    ops.gemm(pw, [bf(x).contiguous()], xres, gamma=gamma)
+    check('x += gamma*(xW+b)', xres, res + gamma * ref, 2e-5)
+
+
+def test_qkv_split_transposed_v(cuda):
+    ops = _ops()
+    g = torch.Generator(device='cuda').manual_seed(2)
+    B, seq, D, heads = 2, 1037, 384, 6
+    seq_pad = ops.pad_to(seq, 8)
+    x = torch.randn(B * seq, D, device=cuda, generator=g)
+    w = torch.randn(3 * D, D, device=cuda, generator=g) / D ** 0.5
+    b = torch.randn(3 * D, device=cuda, generator=g)
+    pw = ops.pack_weight(w, b)
+    qk = torch.zeros(B * seq, 2 * D, dtype=torch.bfloat16, device=cuda)
+    vt = torch.zeros(B * D, seq_pad, dtype=torch.bfloat16, device=cuda)
+    ops.gemm(pw, [bf(x).contiguous()], qk, vt=vt, vt_col0=2 * D, vt_seq=seq, vt_seq_pad=seq_pad)
+    ref = F.linear(rb(x), rb(w), b)
+    check('qk part', qk, ref[:, :2 * D], 1e-2)
+    v_ref = ref[:, 2 * D:].reshape(B, seq, D).permute(0, 2, 1)              # [B, D, seq]
+    check('v transposed', vt.reshape(B, D, seq_pad)[:, :, :seq], v_ref, 1e-2)
+    assert (vt.reshape(B, D, seq_pad)[:, :, seq:] == 0).all()
+
+
+@pytest.mark.parametrize('NB,H,W,cs,N,act', [(2, 14, 19, [64], 64, 'none'), (1, 37, 50, [128], 256, 'relu'),
+                                             (2, 28, 37, [32, 64, 64], 32, 'relu'), (1, 56, 74, [192], 192, 'none'),
+                                             (1, 30, 41, [8], 32, 'relu'), (3, 16, 16, [544], 544, 'relu')])
+def test_conv3x3(cuda, NB, H, W, cs, N, act):
+    ops = _ops()
+    g = torch.Generator(device='cuda').manual_seed(H * W + N)
+    ctot = sum(cs)
+    xs = [torch.randn(NB, c, H, W, device=cuda, generator=g) for c in cs]
+    w = torch.randn(N, ctot, 3, 3, device=cuda, generator=g) / (9 * ctot) ** 0.5
+    b = torch.randn(N, device=cuda, generator=g)
+    pw = ops.pack_weight(w, b, src_c=cs)
+    srcs = [to_nhwc(x) for x in xs]
+    out = torch.zeros(NB, H, W, ops.pad_to(N, 8), dtype=torch.bfloat16, device=cuda)
+    ops.gemm(pw, srcs, out, image=(NB, H, W), act=ops.ACT_RELU if act == 'relu' else ops.ACT_NONE)
+    ref = F.conv2d(torch.cat([rb(x) for x in xs], 1), rb(w), b, padding=1)
+    if act == 'relu':
+        ref = F.relu(ref)
+    check('conv3x3 %s -> %d @%dx%d' % (cs, N, H, W), from_nhwc(out, N), ref, 1e-2)
+
+
+def test_conv3x3_residuals_and_relu_copy(cuda):
+    ops = _ops()
+    g = torch.Generator(device='cuda').manual_seed(5)
+    NB, H, W, Cc = 2, 28, 37, 64
+    x = torch.randn(NB, Cc, H, W, device=cuda, generator=g)
+    r1 = torch.randn(NB, Cc, H, W, device=cuda, generator=g)
+    r2 = torch.randn(NB, Cc, H, W, device=cuda, generator=g)
+    w = torch.randn(Cc, Cc, 3, 3, device=cuda, generator=g) / (9 * Cc) ** 0.5
+    b = torch.randn(Cc, device=cuda, generator=g)
+    pw = ops.pack_weight(w, b)
+    out = torch.zeros(NB, H, W, Cc, dtype=torch.bfloat16, device=cuda)
+    out2 = torch.zeros_like(out)
+    ops.gemm(pw, [to_nhwc(x)], out, image=(NB, H, W), res1=to_nhwc(r1), res2=to_nhwc(r2), out2=out2)
+    ref = F.conv2d(rb(x), rb(w), b, padding=1) + rb(r1) + rb(r2)
+    check('conv + res1 + res2', from_nhwc(out, Cc), ref, 1e-2)
+    check('relu copy', from_nhwc(out2, Cc), F.relu(ref), 1e-2)
+
+
+def test_conv1x1_bn_fold_and_channel_offset(cuda):
+    ops = _ops()
+    g = torch.Generator(device='cuda').manual_seed(6)
+    NB, H, W, Cin, N = 1, 20, 23, 96, 48
+    x = torch.randn(NB, Cin, H, W, device=cuda, generator=g)
+    w = torch.randn(N, Cin, 1, 1, device=cuda, generator=g) / Cin ** 0.5
+    scale = torch.rand(N, device=cuda, generator=g) + 0.5
+    shift = torch.randn(N, device=cuda, generator=g)
+    pw = ops.pack_weight(w, None, scale=scale, shift=shift)
+    out = torch.zeros(NB, H, W, 128, dtype=torch.bfloat16, device=cuda)
+    ops.gemm(pw, [to_nhwc(x)], out, image=(NB, H, W), out_col0=64)
+    ref = F.conv2d(rb(x), rb(w * scale.view(-1, 1, 1, 1))) + shift.view(1, -1, 1, 1)
+    check('conv1x1 + folded BN at col 64', out[..., 64:64 + N].float().permute(0, 3, 1, 2), ref, 1e-2)
+    assert (out[..., :64] == 0).all() and (out[..., 64 + N:] == 0).all()
+
+
+@pytest.mark.parametrize('k,Cin,Cout,H,W', [(4, 48, 48, 5, 7), (2, 96, 96, 9, 6), (4, 256, 256, 28, 37)])
+def test_conv_transpose(cuda, k, Cin, Cout, H, W):
+    ops = _ops()
+    g = torch.Generator(device='cuda').manual_seed(k + Cin)
+    NB = 2
+    x = torch.randn(NB, Cin, H, W, device=cuda, generator=g)
+    w = torch.randn(Cin, Cout, k, k, device=cuda, generator=g) / Cin ** 0.5
+    b = torch.randn(Cout, device=cuda, generator=g)
+    pw = ops.pack_weight_convT(w, b, k)
+    src = to_nhwc(x).reshape(NB * H * W, -1)
+    out = torch.zeros(NB, H * k, W * k, ops.pad_to(Cout, 8), dtype=torch.bfloat16, device=cuda)
+    ops.gemm_convT(pw, src, (NB, H, W), out)
+    ref = F.conv_transpose2d(rb(x), rb(w), b, stride=k)
+    check('convT k%d %d->%d' % (k, Cin, Cout), from_nhwc(out, Cout), ref, 1e-2)
