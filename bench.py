@@ -1,0 +1,268 @@
+"""bench.py — tiles/s (and 4K images/s) of the PatchFusion hot path, Depth-Anything-vitl, 4K, P49 (cai_mode m2).
+
+    python bench.py --gpus 1 --steps K --warmup W                      (this build, CUDA path through the C ABI)
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N --steps K --warmup W
+    python bench.py --impl reference ...                               (reference algorithm on the host cores)
+
+A step = one pass of the hot path over one synthetic 4K image per rank: coarse branch + G2L once, 49 tiles through
+fine branch + guided fusion, scatter-stitch.  Ranks process independent images (weak scaling) and one NCCL
+all-gather assembles the batch of depth canvases.  Prints ONE JSON line (rank 0).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+F_TILE = {'vits': 360.0e9, 'vitb': 1133.9e9, 'vitl': 4029.8e9}     # algorithmic FLOPs / tile   
+F_IMAGE = {'vits': 139.5e9, 'vitb': 404.1e9, 'vitl': 1343.5e9}     # coarse + G2L once per image
+
+
+def peaks():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(tflops_sustained=d['bf16_tflops_sustained'], tflops_burst=d['bf16_tflops'], hbm=d['hbm_gbs'],
+                    source='measured (MEASURED_PEAKS.json)')
+    return dict(tflops_sustained=1400.0, tflops_burst=1590.0, hbm=6650.0, source='fallback (B200_PROFILING.md)')
+
+
+class ClockSampler:
+    QUERY = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
+             'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+             'clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        self.f = tempfile.NamedTemporaryFile('w+', suffix='.csv', delete=False)
+        self.p = None
+        try:
+            self.p = subprocess.Popen(['nvidia-smi', '-i', str(index), '--query-gpu=' + self.QUERY,
+                                       '--format=csv,noheader,nounits', '-lms', '200'], stdout=self.f,
+                                      stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = dict(sm_mhz=None, sm_max_mhz=None, reasons=[])
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        rows = [l.strip().split(', ') for l in open(self.f.name) if l.strip()]
+        os.unlink(self.f.name)
+        sm, reasons = [], set()
+        for r in rows:
+            try:
+                sm.append(float(r[1]))
+                out['sm_max_mhz'] = float(r[2])
+                for name, v in zip(['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'], r[4:8]):
+                    if v.strip().lower().startswith('active'):
+                        reasons.add(name)
+            except Exception:
+                pass
+        if sm:
+            sm.sort()
+            out['sm_mhz'] = sm[len(sm) // 2]
+        out['reasons'] = sorted(reasons)
+        return out
+
+
+def build_inputs(encoder, seed=0):
+    from patchfusion_b200.configs import depth_anything_patchfusion
+    from patchfusion_b200.params import synthetic_state_dict
+    cfg = depth_anything_patchfusion(encoder, image_raw_shape=(2160, 3840), patch_split_num=(4, 4))
+    sd = synthetic_state_dict(cfg, seed=seed)
+    return cfg, sd
+
+
+def cpu_baseline(encoder, cfg, sd, threads, reps=1):
+    """The oracle (a port of the reference algorithm) on the host cores: one micro-batch of ONE tile (fine branch +
+    fusion) after the per-image fixed work; bounded sample, not the product path."""
+    from oracle import pf_oracle as po
+    torch.set_num_threads(threads)
+    g = torch.Generator().manual_seed(1)
+    img = torch.rand(1, 3, 2160, 3840, generator=g)
+    orc = po.Oracle(sd, cfg)
+    P = cfg['patch_process_shape']
+    with torch.no_grad():
+        lr = orc.resizer(img)
+        t0 = time.time()
+        cd, cf = orc.coarse(lr)
+        g2l = po.g2l_all(sd, cf, cfg['guided_fusion'])
+        t_fixed = time.time() - t0
+        tc = po.prepare_tile_cfg((2160, 3840), (4, 4), P)
+        ts = []
+        for r in range(reps):
+            t0 = time.time()
+            orc.tiles(img, [(540 * r, 960)], cd, cf, g2l, 1, tc)
+            ts.append(time.time() - t0)
+    t_tile = min(ts)
+    return dict(value=1.0 / t_tile, unit='tiles/s', cores=threads, kind='port',
+                sample='%s, %d x 1 tile (fine branch + fusion, p=1) of the 4K P49 workload; per-image fixed work '
+                       '(coarse + G2L) took %.1f s and is excluded' % (encoder, reps, t_fixed),
+                s_per_tile=t_tile, s_fixed_per_image=t_fixed)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=3)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--encoder', default='vitl')
+    ap.add_argument('--cai-mode', default='m2')
+    ap.add_argument('--process-num', type=int, default=7)
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--profile', action='store_true', help='per-kernel-family time table to stderr')
+    args = ap.parse_args()
+    rank = int(os.environ.get('RANK', 0))
+    world = int(os.environ.get('WORLD_SIZE', 1))
+    local = int(os.environ.get('LOCAL_RANK', 0))
+    enc = args.encoder
+    n_tiles = {'m1': 16, 'm2': 49}[args.cai_mode]
+    workload = 'Depth-Anything-%s PatchFusion, 4K (2160x3840), P%d (%s, 4x4 split), %d image/rank/step' % (
+        enc, n_tiles, args.cai_mode, 1)
+
+    if args.impl == 'reference':
+        if rank != 0:
+            return
+        cfg, sd = build_inputs(enc)
+        threads = os.cpu_count()
+        t = []
+        for i in range(args.warmup + args.steps):
+            cb = cpu_baseline(enc, cfg, sd, threads, reps=1)
+            if i >= args.warmup:
+                t.append(cb['s_per_tile'])
+            if i == 0 and args.warmup > 1:      # keep the arm within minutes: one warm-up is enough on CPU
+                args.warmup = 1
+        ms = sum(t) / len(t) * 1e3
+        v = 1e3 / ms
+        cb.update(value=v)
+        print(json.dumps(dict(
+            impl='reference', metric='tiles/s', value=v, unit='tiles/s', n_gpus=args.gpus, steps=len(t),
+            warmup=args.warmup, ms_per_step=ms, higher_is_better=True, scaling='weak', vs_baseline=None, dtype='f32',
+            data='synthetic', config=dict(workload=workload, note='each step = 1 tile (bounded sample) on host cores'),
+            cpu_baseline=cb, e2e=dict(value=v, unit='tiles/s', h2d_bytes_per_step=0, d2h_bytes_per_step=0),
+            gpu_launches=0)))
+        return
+
+    from patchfusion_b200 import lib, ops
+    from patchfusion_b200.model import PatchFusion
+    dev = torch.device('cuda', local)
+    torch.cuda.set_device(dev)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group('nccl', device_id=dev)
+    cfg, sd = build_inputs(enc)
+    model = PatchFusion(cfg)
+    model.load_state_dict(sd, strict=True)
+    model = model.to(dev).eval()
+    g = torch.Generator().manual_seed(100 + rank)
+    host_img = torch.rand(1, 3, 2160, 3840, generator=g).pin_memory()
+    RH, RW = model.tile_cfg['patch_reensemble_shape']
+    host_out = torch.empty((1, 1, RH, RW), dtype=torch.float32).pin_memory()
+    gathered = torch.empty((world, RH, RW), dtype=torch.float32, device=dev) if world > 1 else None
+
+    def step(img_dev):
+        lr = model.make_lr(img_dev)
+        y, _ = model(mode='infer', image_lr=lr, image_hr=img_dev, cai_mode=args.cai_mode, process_num=args.process_num)
+        if world > 1:
+            import torch.distributed as dist
+            dist.all_gather_into_tensor(gathered, y[0, 0].contiguous())
+        return y
+
+    def barrier():
+        if world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, k):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(k):
+            fn()
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            import torch.distributed as dist
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = t.item()
+        return ms
+
+    img_dev = host_img.to(dev, non_blocking=True)
+    for _ in range(max(args.warmup, 3)):
+        step(img_dev)
+
+    def e2e_step():
+        d = host_img.to(dev, non_blocking=True)
+        y = step(d)
+        host_out.copy_(y, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    sampler = ClockSampler(local) if rank == 0 else None
+    l0 = lib.launch_count()
+    ms_dev = timed(lambda: step(img_dev), args.steps)
+    launches = lib.launch_count() - l0
+    ms_e2e = timed(e2e_step, args.steps)
+    clocks = sampler.stop() if sampler else {}
+
+    # roofline pass: per-launch CUDA events around every kernel of one more step (not part of the timed value)
+    prof = None
+    if rank == 0:
+        lib.PROFILER = lib.Profiler()
+        step(img_dev)
+        prof = lib.PROFILER.summary()
+        lib.PROFILER = None
+    barrier()
+
+    tiles_per_step = n_tiles * world
+    tps = tiles_per_step * args.steps / (ms_dev / 1e3)
+    tps_e2e = tiles_per_step * args.steps / (ms_e2e / 1e3)
+    if rank != 0:
+        return
+    pk = peaks()
+    gm = prof.get('pf_gemm', dict(ms=1.0, flops=0.0, launches=0))
+    total_ms = sum(v['ms'] for v in prof.values())
+    ach = gm['flops'] / (gm['ms'] / 1e3) / 1e12
+    roof = dict(bound='tensor', achieved=ach, peak=pk['tflops_sustained'], unit='TFLOP/s', frac=ach / pk['tflops_sustained'],
+                traffic=None, kernel='pf_gemm_kernel (tcgen05 implicit GEMM; %d launches/step, %.1f%% of step kernel time)' %
+                (gm['launches'], 100.0 * gm['ms'] / total_ms), peak_source=pk['source'] + ', sustained bf16',
+                whole_step_tflops=(tps / world * F_TILE[enc] + tps / world / n_tiles * F_IMAGE[enc]) / 1e12)
+    if args.profile:
+        for k_, v in sorted(prof.items(), key=lambda kv: -kv[1]['ms']):
+            sys.stderr.write('%-26s %8.2f ms %6d launches %8.1f TF/s\n' % (k_, v['ms'], v['launches'],
+                                                                         v['flops'] / max(v['ms'], 1e-9) / 1e9))
+    cb = None
+    if not args.no_cpu_baseline and world == 1:
+        cb = cpu_baseline(enc, cfg, sd, os.cpu_count())
+    out = dict(
+        metric='tiles/s', value=tps, unit='tiles/s', n_gpus=world, steps=args.steps, warmup=max(args.warmup, 3),
+        ms_per_step=ms_dev / args.steps, higher_is_better=True, scaling='weak', vs_baseline=None, dtype='bf16',
+        data='synthetic', images_per_s=tps / n_tiles,
+        config=dict(workload=workload, process_num=args.process_num, weights='seeded random init (no checkpoints offline)',
+                    l2='working set >> L2: 1.5 GB bf16 weights + ~GBs of activations streamed every step'),
+        e2e=dict(value=tps_e2e, unit='tiles/s', h2d_bytes_per_step=host_img.numel() * 4,
+                 d2h_bytes_per_step=host_out.numel() * 4),
+        gpu_launches=launches, clocks=clocks, roofline=roof, cpu_baseline=cb)
+    print(json.dumps(out))
+
+
+if __name__ == '__main__':
+    main()

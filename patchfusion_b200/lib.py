@@ -108,7 +108,40 @@ def ptr(t):
     return t.data_ptr()
 
 
+class Profiler:
+    """Optional per-launch CUDA-event timing (bench.py's roofline pass); off by default."""
+
+    def __init__(self):
+        self.records = []
+        self.next_flops = 0.0
+
+    def summary(self):
+        torch.cuda.synchronize()
+        out = {}
+        for fam, fl, e0, e1 in self.records:
+            d = out.setdefault(fam, dict(ms=0.0, flops=0.0, launches=0))
+            d['ms'] += e0.elapsed_time(e1)
+            d['flops'] += fl
+            d['launches'] += 1
+        return out
+
+
+PROFILER = None
+
+
 def call(name, *args):
+    if PROFILER is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        fl, PROFILER.next_flops = PROFILER.next_flops, 0.0
+        e0.record()
+        _call(name, *args)
+        e1.record()
+        PROFILER.records.append((name, fl, e0, e1))
+    else:
+        _call(name, *args)
+
+
+def _call(name, *args):
     lib = load()
     conv = []
     for a in args:

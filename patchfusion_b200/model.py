@@ -1,0 +1,294 @@
+"""Drop-in `PatchFusion` for the reference's `estimator.models.patchfusion.PatchFusion` (inference path).
+
+Same constructor dict / `from_pretrained()` / `state_dict()` key layout / `forward(mode='infer', image_lr,
+image_hr, tile_cfg, cai_mode, process_num)` contract and error behaviour as reference
+`estimator/models/patchfusion.py:55-453` + `estimator/models/baseline_pretrain.py:91-331`; the arithmetic runs on
+libpf_b200 (sm_100a) through `Engine`.  There is no CPU path: calling forward on CPU tensors raises.
+"""
+import math
+import random
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from .params import ParamTree, _get, state_layout, synthetic_state_dict, relative_position_index
+
+try:
+    from huggingface_hub import PyTorchModelHubMixin
+except Exception:                                   # pragma: no cover
+    class PyTorchModelHubMixin:                     # minimal stand-in when huggingface_hub is absent
+        pass
+
+
+class AttrDict(dict):
+    """Attribute-style view of nested config dicts (the reference reads `config.coarse_branch.type`)."""
+
+    def __init__(self, d=None):
+        super().__init__()
+        for k, v in (d or {}).items():
+            self[k] = AttrDict(v) if isinstance(v, dict) else v
+
+    def __getattr__(self, k):
+        try:
+            return self[k]
+        except KeyError:
+            raise AttributeError(k)
+
+    def __setattr__(self, k, v):
+        self[k] = v
+
+    def to_dict(self):
+        return {k: (v.to_dict() if isinstance(v, AttrDict) else v) for k, v in self.items()}
+
+    def to_json_file(self, path):                   # `tools/convert_huggingface.py:79`
+        import json
+        with open(path, 'w') as f:
+            json.dump(self.to_dict(), f, indent=2)
+
+
+class Resize:
+    """`model.resizer`: bilinear align_corners=True to patch_process_shape (depth_anything/transform.py:127-129 with
+    keep_aspect_ratio=False => always exactly (h, w), as used at patchfusion.py:94)."""
+
+    def __init__(self, width, height):
+        self.w, self.h = width, height
+
+    def __call__(self, x):
+        return nn.functional.interpolate(x, (int(self.h), int(self.w)), mode='bilinear', align_corners=True)
+
+
+def _gauss_kernel(ksize, sigma):
+    i = np.arange(ksize, dtype=np.float64) - (ksize - 1) / 2
+    k = np.exp(-(i * i) / (2.0 * sigma * sigma))
+    return (k / k.sum()).astype(np.float32)
+
+
+def generatemask(size):
+    """Gaussian blend mask of `estimator/models/utils.py:38-47` without OpenCV: 1 inside the central 80 %, separable
+    Gaussian blur (k = 2*ceil(2*sigma)+1, sigma = int(H/16), BORDER_REFLECT_101), min-max normalised."""
+    H, W = int(size[0]), int(size[1])
+    mask = np.zeros((H, W), dtype=np.float32)
+    sigma = int(H / 16)
+    k = int(2 * np.ceil(2 * int(H / 16)) + 1)
+    mask[int(0.1 * H):H - int(0.1 * H), int(0.1 * W):W - int(0.1 * W)] = 1
+    ker = _gauss_kernel(k, float(sigma))
+    r = k // 2
+
+    def blur_rows(a):       # convolve along axis 1
+        p = np.pad(a, ((0, 0), (r, r)), mode='reflect')
+        cs = np.zeros_like(a, dtype=np.float32)
+        for j in range(k):
+            cs += ker[j] * p[:, j:j + a.shape[1]]
+        return cs
+
+    m = blur_rows(mask)
+    m = blur_rows(m.T.copy()).T
+    m = (m - m.min()) / (m.max() - m.min())
+    return m.astype(np.float32)
+
+
+class PatchFusion(ParamTree, PyTorchModelHubMixin):
+    def __init__(self, config):
+        nn.Module.__init__(self)
+        if not isinstance(config, dict) and hasattr(config, 'to_dict'):
+            config = config.to_dict()
+        config = AttrDict(dict(config))
+        # the HF-dict constructor branch of the reference (patchfusion.py:70-78)
+        config.load_branch = bool(config.get('load_branch', False))
+        self.config = config
+        self.min_depth = config.min_depth
+        self.max_depth = config.max_depth
+        self.patch_process_shape = config.patch_process_shape
+        self.tile_cfg = self.prepare_tile_cfg(config.image_raw_shape, config.patch_split_num)
+        self.coarse_branch_cfg = config.coarse_branch
+        for br in (config.coarse_branch, config.fine_branch):
+            if br.type not in ('ZoeDepth', 'DA-ZoeDepth'):
+                raise NotImplementedError
+        self.resizer = Resize(config.patch_process_shape[1], config.patch_process_shape[0])
+        self._build_tree(state_layout(config))      # raises ValueError / NotImplementedError like the reference
+        self.consistency_training = False
+        self._engine = None
+        self._mask_cache = {}
+        if config.load_branch:
+            for which, path in zip(('coarse_branch', 'fine_branch'), config.pretrain_model):
+                sd = torch.load(path, map_location='cpu')['model_state_dict']
+                getattr(self, which).load_state_dict(sd, strict=True)
+        # constant buffers exactly as the reference constructs them
+        with torch.no_grad():
+            for name, buf in self.named_buffers():
+                if name.endswith('relative_position_index'):
+                    buf.copy_(relative_position_index())
+                elif name.endswith('k_idx'):
+                    buf.copy_(torch.arange(buf.numel()).view(buf.shape))
+                elif name.endswith('K_minus_1'):
+                    buf.fill_(float(_get(config.coarse_branch, 'n_bins', 64) - 1))
+                elif name.endswith('running_var'):
+                    buf.fill_(1.0)
+
+    # ------------------------------------------------------------------ reference API surface
+    def prepare_tile_cfg(self, image_raw_shape, patch_split_num):
+        assert image_raw_shape[0] % (2 * patch_split_num[0]) == 0, \
+            'image height should be divisible by 2 * patch_split_num[0]'
+        assert image_raw_shape[1] % (2 * patch_split_num[1]) == 0, \
+            'image width should be divisible by 2 * patch_split_num[1]'
+        pps = self.patch_process_shape
+        patch_reensemble_shape = (pps[0] * patch_split_num[0], pps[1] * patch_split_num[1])
+        patch_raw_shape = (image_raw_shape[0] // patch_split_num[0], image_raw_shape[1] // patch_split_num[1])
+        return {'patch_split_num': patch_split_num, 'patch_reensemble_shape': patch_reensemble_shape,
+                'patch_raw_shape': patch_raw_shape, 'image_raw_shape': image_raw_shape,
+                'raw_h_split_point': [int(patch_raw_shape[0] * i) for i in range(patch_split_num[0])],
+                'raw_w_split_point': [int(patch_raw_shape[1] * i) for i in range(patch_split_num[1])]}
+
+    def load_dict(self, dict):
+        return self.load_state_dict(dict, strict=False)
+
+    def get_save_dict(self):
+        return {k: v for k, v in self.state_dict().items() if 'coarse_branch' not in k and 'fine_branch' not in k}
+
+    def load_state_dict(self, *a, **kw):
+        self._engine = None
+        return super().load_state_dict(*a, **kw)
+
+    def _apply(self, fn, *a, **kw):
+        self._engine = None
+        return super()._apply(fn, *a, **kw)
+
+    def init_synthetic_weights(self, seed=0):
+        """Seeded random weights (no checkpoints are reachable offline)."""
+        self.load_state_dict(synthetic_state_dict(self.config, seed=seed), strict=True)
+        return self
+
+    # ------------------------------------------------------------------ engine plumbing
+    def engine(self, device=None):
+        from .engine import Engine
+        if self._engine is None:
+            p = next(self.parameters())
+            if not p.is_cuda:
+                raise RuntimeError('PatchFusion (B200): the hot path runs on libpf_b200 only; move the model to a '
+                                   'CUDA device (there is no CPU fallback)')
+            self._engine = Engine(self.config, self.state_dict(), p.device)
+        return self._engine
+
+    @torch.no_grad()
+    def make_lr(self, image_hr):
+        """`image_lr = model.resizer(image)` of `tools/test_single_forward.py:13-14` on the device (same bilinear
+        align_corners=True resample, pf_crop_resize with one whole-image tile)."""
+        from . import ops
+        img = image_hr[0].float().contiguous()
+        H, W = img.shape[-2:]
+        ph, pw = self.patch_process_shape
+        out = torch.empty((1, 3, ph, pw), dtype=torch.float32, device=img.device)
+        org = torch.zeros((1, 2), dtype=torch.int32, device=img.device)
+        ops.call('pf_crop_resize', img, H, W, org, 1, H, W, ph, pw, out, ops.stream_ptr())
+        return out
+
+    def _mask(self, size, device):
+        key = (tuple(size), str(device))
+        if key not in self._mask_cache:
+            self._mask_cache[key] = torch.tensor(generatemask(size) + 1e-3, device=device)
+        return self._mask_cache[key]
+
+    # ------------------------------------------------------------------ stage-level entry points (NCHW fp32 views)
+    @staticmethod
+    def _nchw(m):
+        return m.t[..., :m.C].float().permute(0, 3, 1, 2).contiguous()
+
+    @torch.no_grad()
+    def coarse_forward(self, image_lr):
+        d, feats = self.engine().branch('coarse', image_lr.float().contiguous())
+        return d[:, None].clone(), [self._nchw(f) for f in feats]
+
+    @torch.no_grad()
+    def fine_forward(self, image_hr_crop):
+        d, feats = self.engine().branch('fine', image_hr_crop.float().contiguous())
+        return d[:, None].clone(), [self._nchw(f) for f in feats]
+
+    # ------------------------------------------------------------------ tiling
+    def _tile_batch(self, eng, image_hr, raw_origins, coarse, tile_cfg, process_num):
+        """Fused depth for tiles at raw (y, x) origins: yields (fp32 [p, ph, pw] buffer, p) per micro-batch; the
+        buffer is reused by the next micro-batch, so consume it (stitch) before advancing."""
+        from . import ops
+        cd, cf, g2l = coarse
+        dev = image_hr.device
+        H, W = tile_cfg['image_raw_shape']
+        h, w = tile_cfg['patch_raw_shape']
+        ph, pw = self.patch_process_shape
+        fx = np.float32(1 / W * pw)
+        fy = np.float32(1 / H * ph)
+        for s in range(0, len(raw_origins), process_num):
+            chunk = raw_origins[s:s + process_num]
+            T = len(chunk)
+            org = torch.tensor(chunk, dtype=torch.int32, device=dev)
+            bx = np.array([[np.float32(x) * fx, np.float32(y) * fy, np.float32(x + w) * fx, np.float32(y + h) * fy]
+                           for (y, x) in chunk], dtype=np.float32)
+            boxes = torch.tensor(bx, device=dev)
+            crops = eng.buf('tile.crops', (T, 3, ph, pw), torch.float32)
+            ops.call('pf_crop_resize', image_hr, H, W, org, T, h, w, ph, pw, crops, ops.stream_ptr())
+            fd, ff = eng.branch('fine', crops)
+            pred = eng.fusion(crops, boxes, fd, ff, cd, cf, g2l)
+            yield pred, T
+
+    @torch.no_grad()
+    def forward(self, mode, image_lr, image_hr, depth_gt=None, crops_image_hr=None, crop_depths=None, bboxs=None,
+                tile_cfg=None, cai_mode='m1', process_num=4):
+        if mode == 'train':
+            raise NotImplementedError('training is out of scope of the B200 hot-path build (SURVEY.md §2 rows 10,12)')
+        from . import ops
+        if tile_cfg is None:
+            tile_cfg = self.tile_cfg
+        else:
+            tile_cfg = self.prepare_tile_cfg(tile_cfg['image_raw_shape'], tile_cfg['patch_split_num'])
+        assert image_hr.shape[0] == 1
+        eng = self.engine()
+        dev = image_hr.device
+        st = ops.stream_ptr
+        img = image_hr[0].float().contiguous()
+        H, W = tile_cfg['image_raw_shape']
+        assert tuple(img.shape[-2:]) == (H, W), 'image_hr must already be at image_raw_shape'
+        h, w = tile_cfg['patch_raw_shape']
+        ph, pw = self.patch_process_shape
+        RH, RW = tile_cfg['patch_reensemble_shape']
+
+        cd, cf = eng.branch('coarse', image_lr.float().contiguous())
+        cd = cd[0].clone()
+        cf = [type(f)(f.t.clone(), f.C) for f in cf]       # coarse maps outlive the fine branch's buffer reuse
+        g2l = eng.g2l(cf)
+        coarse = (cd, cf, g2l)
+
+        num = torch.zeros((RH, RW), dtype=torch.float32, device=dev)
+        den = torch.zeros((RH, RW), dtype=torch.float32, device=dev)
+        mask = self._mask((ph, pw), dev)
+        offsets = [((0, 0), (0, 0))]
+        if cai_mode == 'm2' or cai_mode[0] == 'r':
+            offsets += [((0, w // 2), (0, pw // 2)), ((h // 2, 0), (ph // 2, 0)), ((h // 2, w // 2), (ph // 2, pw // 2))]
+        # The regular passes (baseline_pretrain.py:221-331, patchfusion.py:417-439) are independent tiles whose
+        # stitch is a commutative weighted sum, so all passes are flattened into one tile list and micro-batched.
+        raw, proc = [], []
+        for (oy, ox), (py, px) in offsets:
+            assert ox >= 0 and oy >= 0
+            ny, nx = (H - oy) // h, (W - ox) // w
+            raw += [(h * a + oy, w * b + ox) for a in range(ny) for b in range(nx)]
+            proc += [(ph * a + py, pw * b + px) for a in range(ny) for b in range(nx)]
+        done = 0
+        for pred, T in self._tile_batch(eng, img, raw, coarse, tile_cfg, process_num):
+            org = torch.tensor(proc[done:done + T], dtype=torch.int32, device=dev)
+            ops.call('pf_stitch_accumulate', num, den, RH, RW, pred, T, ph, pw, org, mask, 0, 0, st())
+            done += T
+        if cai_mode[0] == 'r':
+            mask = self._mask((h, w), dev)
+            n2 = torch.zeros((H, W), dtype=torch.float32, device=dev)
+            d2 = torch.zeros((H, W), dtype=torch.float32, device=dev)
+            ops.call('pf_stitch_resize', num, den, RH, RW, H, W, n2, d2, st())
+            num, den = n2, d2
+            for _ in range(int(cai_mode[1:]) // process_num):
+                ys = [random.randint(0, H - h - 1) for _ in range(process_num)]     # baseline_pretrain.py:155-156
+                x0 = random.randint(0, W - w - 1)
+                raw = [(y, x0) for y in ys]
+                for pred, T in self._tile_batch(eng, img, raw, coarse, tile_cfg, process_num):
+                    org = torch.tensor(raw, dtype=torch.int32, device=dev)
+                    ops.call('pf_stitch_accumulate', num, den, H, W, pred, T, ph, pw, org, mask, h, w, st())
+        out = torch.empty_like(num)
+        ops.call('pf_stitch_finalize', num, den, ops.C.c_int64(num.numel()), out, st())
+        depth = out[None, None]
+        return depth, {'rgb': image_lr, 'depth_pred': depth, 'depth_gt': depth_gt}

@@ -127,6 +127,9 @@ def gemm(pw, srcs, out, *, image=None, ps_image=None, M=None, act=ACT_NONE, res1
     if vt is not None:
         d.vt = vt.data_ptr()
         d.vt_col0, d.vt_seq, d.vt_seq_pad, d.vt_dim = vt_col0, vt_seq, vt_seq_pad, pw.N - vt_col0
+    if lib.PROFILER is not None:
+        n_true = pw.ps_cout * pw.ps * pw.ps if pw.ps > 1 else pw.N
+        lib.PROFILER.next_flops = 2.0 * rows * sum(cs) * pw.taps * n_true
     call('pf_gemm', C.byref(d), stream_ptr())
     return d
 
@@ -143,6 +146,8 @@ def layernorm(x, w, b, eps, out, rows=None, C_=None):
 
 
 def attention(qk, vt, B, seq, seq_pad, heads, scale, out):
+    if lib.PROFILER is not None:
+        lib.PROFILER.next_flops = 4.0 * B * heads * seq * seq * 64
     call('pf_attention', qk, qk.shape[-1], vt, B, seq, seq_pad, heads, C.c_float(scale), out, out.shape[-1],
          stream_ptr())
 

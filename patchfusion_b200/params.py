@@ -236,6 +236,31 @@ class ParamTree(nn.Module):
                 node.register_buffer(parts[-1], t)
 
 
+# (pattern, gain) in priority order: gain 2 where a ReLU follows (variance preserving), < 1 on residual branches and
+# after sums so the DPT / U-Net activations stay O(1) and the log-binomial head works in its smooth regime.
+_GAINS = [
+    ('resConfUnit1.conv2', 0.25), ('resConfUnit2.conv2', 0.25), ('resConfUnit', 2.0),
+    ('refinenet', 0.5),                        # FFB out_conv after path + skip
+    ('layer1_rn', 1.0), ('layer2_rn', 1.0), ('layer3_rn', 1.0), ('layer4_rn', 1.0),
+    ('projects', 1.0), ('resize_layers', 1.0),
+    ('output_conv1', 1.0), ('output_conv2.0', 2.0), ('output_conv2.2', 1.0),
+    ('conditional_log_binomial.mlp.0', 1.0), ('conditional_log_binomial.mlp.2', 1.0),
+    ('attractors', None), ('_net.0', 2.0), ('_net.2', 1.0),
+    ('fusion_conv_list', 1.0), ('double_conv', 2.0), ('embed_proj', 1.0),
+    ('patch_embed', 1.0), ('conv2.weight', 1.0),
+    ('attn.qkv', 1.0), ('attn.proj', 1.0), ('mlp.fc1', 2.0), ('mlp.fc2', 1.0),
+]
+
+
+def _gain(key):
+    for pat, g in _GAINS:
+        if pat in key:
+            if g is None:                      # attractor MLPs: '_net.0' relu, '_net.2' softplus head
+                return 2.0 if '_net.0' in key else 1.0
+            return g
+    raise AssertionError('no init rule for ' + key)
+
+
 def synthetic_state_dict(config, seed=0, dtype=torch.float32):
     """Seeded random weights with O(1) activations through the whole network.
 
@@ -279,16 +304,11 @@ def synthetic_state_dict(config, seed=0, dtype=torch.float32):
             t = 1.0 + rn(shape, 0.1)
         elif leaf == 'weight':
             fan_in = 1
-            for s in shape[1:]:
-                fan_in *= s
+            for s_ in shape[1:]:
+                fan_in *= s_
             if 'resize_layers.0' in key or 'resize_layers.1' in key:
                 fan_in = shape[0]                                # ConvTranspose k==s: one tap per output pixel
-            gain = 2.0 if ('conv' in key or '_net' in key or 'fusion' in key or 'depth_head' in key) else 1.0
-            if 'resConfUnit' in key and key.endswith('conv2.weight'):
-                gain = 0.5
-            if key.endswith('_net.2.weight') and 'attractors' in key:
-                gain = 4.0
-            t = rn(shape, math.sqrt(gain / fan_in))
+            t = rn(shape, math.sqrt(_gain(key) / fan_in))
         else:
             raise AssertionError(key)
         sd[key] = t.to(dt if dt != torch.float32 else dtype)

@@ -1,0 +1,67 @@
+"""The C-ABI library: builds for sm_100a without a GPU, exports every symbol include/pf_b200.h declares, and the
+ctypes mirror of pf_gemm_desc has the header's layout.  No compute calls here."""
+import os
+import re
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HDR = os.path.join(ROOT, 'include', 'pf_b200.h')
+
+
+def _declared():
+    src = re.sub(r'/\*.*?\*/', '', open(HDR).read(), flags=re.S)
+    return sorted(set(re.findall(r'\b(pf_[A-Za-z0-9_]+)\s*\(', src)))
+
+
+def test_library_builds_and_exports_header_symbols():
+    from patchfusion_b200 import build, lib
+    path = build.build()
+    assert os.path.exists(path)
+    out = subprocess.check_output(['nm', '-D', '--defined-only', path], text=True)
+    exported = set(l.split()[-1] for l in out.splitlines() if l.strip())
+    declared = _declared()
+    assert len(declared) >= 25
+    missing = [s for s in declared if s not in exported]
+    assert not missing, missing
+    assert sorted(lib.EXPORTS) == declared
+    h = lib.load()
+    assert h.pf_version() >= 100
+
+
+def test_sass_is_blackwell_native():
+    from patchfusion_b200 import build
+    path = build.build()
+    sass = subprocess.run(['cuobjdump', '-sass', path], capture_output=True, text=True).stdout
+    assert 'UTCHMMA' in sass or 'UTCMMA' in sass or 'UTC' in sass, 'no tcgen05.mma in SASS'
+    assert 'UTMALDG' in sass, 'no TMA loads in SASS'
+    assert 'LDTM' in sass, 'no tcgen05.ld in SASS'
+
+
+def test_gemm_desc_layout(tmp_path):
+    import ctypes
+    from patchfusion_b200.lib import GemmDesc
+    fields = [f[0] for f in GemmDesc._fields_]
+    prog = '#include <stdio.h>\n#include <stddef.h>\n#include "%s"\nint main(){' % HDR
+    for f in fields:
+        prog += 'printf("%s %%zu\\n", offsetof(pf_gemm_desc, %s));' % (f, f)
+    prog += 'printf("sizeof %zu\\n", sizeof(pf_gemm_desc));return 0;}'
+    c = tmp_path / 'off.c'
+    c.write_text(prog)
+    exe = tmp_path / 'off'
+    subprocess.check_call(['gcc', str(c), '-o', str(exe)])
+    for line in subprocess.check_output([str(exe)], text=True).splitlines():
+        k, v = line.split()
+        if k == 'sizeof':
+            assert int(v) == ctypes.sizeof(GemmDesc)
+        else:
+            assert getattr(GemmDesc, k).offset == int(v), k
+
+
+def test_no_fallback_when_library_missing(monkeypatch, tmp_path):
+    from patchfusion_b200 import lib
+    monkeypatch.setattr(lib, '_lib', None)
+    monkeypatch.setattr(lib, 'LIB_PATH', str(tmp_path / 'nope.so'))
+    with pytest.raises(lib.PFError):
+        lib.load()
