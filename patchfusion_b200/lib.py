@@ -146,6 +146,8 @@ def _call(name, *args):
     conv = []
     for a in args:
         if isinstance(a, torch.Tensor):
+            if not a.is_contiguous():
+                raise PFError('%s: non-contiguous tensor passed as a raw pointer' % name)
             conv.append(C.c_void_p(ptr(a)))
         elif a is None:
             conv.append(None)

@@ -85,7 +85,7 @@ def generatemask(size):
     m = blur_rows(mask)
     m = blur_rows(m.T.copy()).T
     m = (m - m.min()) / (m.max() - m.min())
-    return m.astype(np.float32)
+    return np.ascontiguousarray(m, dtype=np.float32)
 
 
 class PatchFusion(ParamTree, PyTorchModelHubMixin):
@@ -186,7 +186,7 @@ class PatchFusion(ParamTree, PyTorchModelHubMixin):
     def _mask(self, size, device):
         key = (tuple(size), str(device))
         if key not in self._mask_cache:
-            self._mask_cache[key] = torch.tensor(generatemask(size) + 1e-3, device=device)
+            self._mask_cache[key] = torch.tensor(generatemask(size) + 1e-3, device=device).contiguous()
         return self._mask_cache[key]
 
     # ------------------------------------------------------------------ stage-level entry points (NCHW fp32 views)

@@ -38,7 +38,7 @@ def test_tile_plan_counts():
 def test_blend_mask_matches_opencv(size):
     from oracle.pf_oracle import gaussian_mask
     a, b = generatemask(size), gaussian_mask(size)
-    assert a.dtype == np.float32 and a.shape == tuple(size)
+    assert a.dtype == np.float32 and a.shape == tuple(size) and a.flags['C_CONTIGUOUS']
     assert np.abs(a - b).max() < 5e-6
     assert a.min() == 0.0 and a.max() == 1.0
 
