@@ -8,7 +8,7 @@ CSRC = os.path.join(HERE, 'csrc')
 SOURCES = ['pf_api.cu', 'pf_gemm.cu', 'pf_attn.cu', 'pf_elem.cu']
 LIB = os.path.join(HERE, 'libpf_b200.so')
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
-              '-Xcompiler', '-fPIC', '--use_fast_math=false'.replace('--use_fast_math=false', '-Xcompiler=-O2')]
+              '-Xcompiler', '-fPIC']
 
 
 def _stale():
@@ -37,7 +37,7 @@ def build(force=False, verbose=False):
             sys.stderr.write(out)
         if p.returncode != 0:
             raise RuntimeError('nvcc failed on %s' % src)
-    cmd = [nvcc, '-shared', '-o', LIB] + objs + ['-lcudart']
+    cmd = [nvcc, '-gencode', 'arch=compute_100a,code=sm_100a', '-shared', '-o', LIB] + objs + ['-lcudart']
     subprocess.check_call(cmd)
     return LIB
 

@@ -24,33 +24,48 @@ __device__ __forceinline__ float warp_sum(float v) {
 static inline unsigned nblocks(long long n, int threads) { return static_cast<unsigned>((n + threads - 1) / threads); }
 
 // ------------------------------------------------------------------------------------------------ LayerNorm
-// one warp per row; two-pass (mean, then centred variance) in fp32 like ATen.
+// one warp per row; the row lives in registers (C <= 1024) so HBM is touched once: mean, centred variance (two-pass
+// like ATen), normalise, bf16 store.
+__device__ __forceinline__ void ln_row(const float* __restrict__ xr, const float* __restrict__ w,
+                                       const float* __restrict__ b, float eps, int C, bf16* __restrict__ orow, int lane) {
+  float4 v[8];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    int c = lane * 4 + i * 128;
+    if (c < C) { v[i] = *reinterpret_cast<const float4*>(xr + c); s += v[i].x + v[i].y + v[i].z + v[i].w; }
+  }
+  const float mean = warp_sum(s) / C;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    int c = lane * 4 + i * 128;
+    if (c < C) {
+      float a = v[i].x - mean, bb = v[i].y - mean, cc = v[i].z - mean, d = v[i].w - mean;
+      q += a * a + bb * bb + cc * cc + d * d;
+    }
+  }
+  const float rstd = rsqrtf(warp_sum(q) / C + eps);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    int c = lane * 4 + i * 128;
+    if (c < C) {
+      float4 g = __ldg(reinterpret_cast<const float4*>(w + c));
+      float4 be = __ldg(reinterpret_cast<const float4*>(b + c));
+      uint2 pk = make_uint2(pack_bf16((v[i].x - mean) * rstd * g.x + be.x, (v[i].y - mean) * rstd * g.y + be.y),
+                            pack_bf16((v[i].z - mean) * rstd * g.z + be.z, (v[i].w - mean) * rstd * g.w + be.w));
+      *reinterpret_cast<uint2*>(orow + c) = pk;
+    }
+  }
+}
+
 __global__ void layernorm_kernel(const float* __restrict__ x, int x_ld, const float* __restrict__ w,
                                  const float* __restrict__ b, float eps, int rows, int C, bf16* __restrict__ out,
                                  int out_ld) {
   int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  int lane = threadIdx.x & 31;
   if (row >= rows) return;
-  const float* xr = x + static_cast<long long>(row) * x_ld;
-  float s = 0.f;
-  for (int c = lane * 4; c < C; c += 128) { float4 v = *reinterpret_cast<const float4*>(xr + c); s += v.x + v.y + v.z + v.w; }
-  float mean = warp_sum(s) / C;
-  float q = 0.f;
-  for (int c = lane * 4; c < C; c += 128) {
-    float4 v = *reinterpret_cast<const float4*>(xr + c);
-    float a = v.x - mean, bb = v.y - mean, cc = v.z - mean, d = v.w - mean;
-    q += a * a + bb * bb + cc * cc + d * d;
-  }
-  float rstd = rsqrtf(warp_sum(q) / C + eps);
-  bf16* orow = out + static_cast<long long>(row) * out_ld;
-  for (int c = lane * 4; c < C; c += 128) {
-    float4 v = *reinterpret_cast<const float4*>(xr + c);
-    float4 g = *reinterpret_cast<const float4*>(w + c);
-    float4 be = *reinterpret_cast<const float4*>(b + c);
-    uint2 pk = make_uint2(pack_bf16((v.x - mean) * rstd * g.x + be.x, (v.y - mean) * rstd * g.y + be.y),
-                          pack_bf16((v.z - mean) * rstd * g.z + be.z, (v.w - mean) * rstd * g.w + be.w));
-    *reinterpret_cast<uint2*>(orow + c) = pk;
-  }
+  ln_row(x + static_cast<long long>(row) * x_ld, w, b, eps, C, out + static_cast<long long>(row) * out_ld,
+         threadIdx.x & 31);
 }
 
 // LayerNorm into the zero-padded (Hp x Wp) Swin token grid.
@@ -66,25 +81,7 @@ __global__ void swin_norm_pad_kernel(const float* __restrict__ x, const float* _
     for (int c = lane * 4; c < C; c += 128) *reinterpret_cast<uint2*>(orow + c) = make_uint2(0u, 0u);
     return;
   }
-  const float* xr = x + (static_cast<long long>(y) * W + xx) * C;
-  float s = 0.f;
-  for (int c = lane * 4; c < C; c += 128) { float4 v = *reinterpret_cast<const float4*>(xr + c); s += v.x + v.y + v.z + v.w; }
-  float mean = warp_sum(s) / C;
-  float q = 0.f;
-  for (int c = lane * 4; c < C; c += 128) {
-    float4 v = *reinterpret_cast<const float4*>(xr + c);
-    float a = v.x - mean, bb = v.y - mean, cc = v.z - mean, d = v.w - mean;
-    q += a * a + bb * bb + cc * cc + d * d;
-  }
-  float rstd = rsqrtf(warp_sum(q) / C + eps);
-  for (int c = lane * 4; c < C; c += 128) {
-    float4 v = *reinterpret_cast<const float4*>(xr + c);
-    float4 g = *reinterpret_cast<const float4*>(w + c);
-    float4 be = *reinterpret_cast<const float4*>(b + c);
-    uint2 pk = make_uint2(pack_bf16((v.x - mean) * rstd * g.x + be.x, (v.y - mean) * rstd * g.y + be.y),
-                          pack_bf16((v.z - mean) * rstd * g.z + be.z, (v.w - mean) * rstd * g.w + be.w));
-    *reinterpret_cast<uint2*>(orow + c) = pk;
-  }
+  ln_row(x + (static_cast<long long>(y) * W + xx) * C, w, b, eps, C, orow, lane);
 }
 
 // ------------------------------------------------------------------------------------------------ ViT input
@@ -572,7 +569,7 @@ extern "C" {
 
 int pf_layernorm(const float* x, int32_t x_ld, const float* w, const float* b, float eps, int32_t rows, int32_t C,
                  void* out, int32_t out_ld, void* stream) {
-  if (C % 4 || x_ld % 4 || out_ld % 4) return set_error("pf_layernorm: C and strides must be multiples of 4");
+  if (C % 4 || x_ld % 4 || out_ld % 4 || C > 1024) return set_error("pf_layernorm: C (<= 1024) and strides must be multiples of 4");
   layernorm_kernel<<<nblocks(rows, 8), 256, 0, ST>>>(x, x_ld, w, b, eps, rows, C, static_cast<bf16*>(out), out_ld);
   return check_launch("layernorm_kernel");
 }
@@ -670,7 +667,7 @@ int pf_g2l_embed(const void* feat, int32_t feat_ld, const float* ape, int32_t n,
 
 int pf_swin_norm_pad(const float* x, const float* w, const float* b, float eps, int32_t H, int32_t W, int32_t Hp,
                      int32_t Wp, int32_t C, void* out, void* stream) {
-  if (C % 4) return set_error("pf_swin_norm_pad: C must be a multiple of 4");
+  if (C % 4 || C > 1024) return set_error("pf_swin_norm_pad: C (<= 1024) must be a multiple of 4");
   swin_norm_pad_kernel<<<nblocks(static_cast<long long>(Hp) * Wp, 8), 256, 0, ST>>>(x, w, b, eps, H, W, Hp, Wp, C,
                                                                                      static_cast<bf16*>(out));
   return check_launch("swin_norm_pad_kernel");

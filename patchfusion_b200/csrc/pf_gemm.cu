@@ -60,11 +60,116 @@ __device__ __forceinline__ TileCoord decode_tile(const GemmDesc& d, int t) {
   return c;
 }
 
-__device__ __forceinline__ float apply_act(float v, int act) {
-  if (act == PF_ACT_RELU) return fmaxf(v, 0.0f);
-  if (act == PF_ACT_GELU) return gelu_erf(v);
-  if (act == PF_ACT_SOFTPLUS) return softplus(v);
-  return v;
+
+// One 32-column chunk of one accumulator row: bias -> activation -> residuals -> store.  FULL == all 32 columns exist
+// (vector loads/stores, no predication); the tail variant predicates every column but keeps all indices static so
+// f[] stays in registers.
+template <bool FULL>
+__device__ __forceinline__ void epilogue_chunk(const GemmDesc& d, float (&f)[32], long long orow, int ncol, int lcol,
+                                               int nvalid) {
+  if (d.bias != nullptr) {
+    if (FULL) {
+      const float4* bp = reinterpret_cast<const float4*>(d.bias + lcol);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float4 b = __ldg(bp + j);
+        f[4 * j] += b.x; f[4 * j + 1] += b.y; f[4 * j + 2] += b.z; f[4 * j + 3] += b.w;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) if (j < nvalid) f[j] += __ldg(d.bias + lcol + j);
+    }
+  }
+  if (d.act == PF_ACT_RELU) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.0f);
+  } else if (d.act == PF_ACT_GELU) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) f[j] = gelu_erf(f[j]);
+  } else if (d.act == PF_ACT_SOFTPLUS) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) f[j] = softplus(f[j]);
+  }
+#pragma unroll
+  for (int rsel = 0; rsel < 2; ++rsel) {
+    const __nv_bfloat16* rbase = rsel == 0 ? d.res1 : d.res2;
+    if (rbase == nullptr) continue;
+    const __nv_bfloat16* rp = rbase + orow * d.res_ld + lcol;
+    if (FULL) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        uint4 u = __ldg(reinterpret_cast<const uint4*>(rp) + j);
+        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          float2 t = __bfloat1622float2(h[e]);
+          f[8 * j + 2 * e] += t.x; f[8 * j + 2 * e + 1] += t.y;
+        }
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) if (j < nvalid) f[j] += __bfloat162float(rp[j]);
+    }
+  }
+  const int oc = lcol + d.out_col0;      // physical output column
+  if (d.vt != nullptr && ncol >= d.vt_col0) {
+    // attention V written transposed: vt[(b*heads + h)*64 + dd][token]
+    const int m = static_cast<int>(orow);
+    const int b = m / d.vt_seq, tok = m - b * d.vt_seq;
+    __nv_bfloat16* vp = d.vt + (static_cast<long long>(b) * d.vt_dim + (ncol - d.vt_col0)) * d.vt_seq_pad + tok;
+#pragma unroll
+    for (int j = 0; j < 32; ++j)
+      if (FULL || j < nvalid) vp[static_cast<long long>(j) * d.vt_seq_pad] = __float2bfloat16(f[j]);
+  } else if (d.gamma != nullptr) {
+    // x <- x + gamma * (acc + bias): fp32 residual stream updated in place
+    float* xp = reinterpret_cast<float*>(d.out) + orow * d.out_ld + oc;
+    if (FULL) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) {
+        float4 xv = *reinterpret_cast<float4*>(xp + j);
+        float4 g = __ldg(reinterpret_cast<const float4*>(d.gamma + lcol + j));
+        xv.x += g.x * f[j]; xv.y += g.y * f[j + 1]; xv.z += g.z * f[j + 2]; xv.w += g.w * f[j + 3];
+        *reinterpret_cast<float4*>(xp + j) = xv;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) if (j < nvalid) xp[j] += __ldg(d.gamma + lcol + j) * f[j];
+    }
+  } else if (d.out_f32) {
+    float* op = reinterpret_cast<float*>(d.out) + orow * d.out_ld + oc;
+    if (FULL) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 4)
+        *reinterpret_cast<float4*>(op + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) if (j < nvalid) op[j] = f[j];
+    }
+  } else {
+    __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(d.out) + orow * d.out_ld + oc;
+    if (FULL) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 8)
+        *reinterpret_cast<uint4*>(op + j) = make_uint4(pack_bf16(f[j], f[j + 1]), pack_bf16(f[j + 2], f[j + 3]),
+                                                        pack_bf16(f[j + 4], f[j + 5]), pack_bf16(f[j + 6], f[j + 7]));
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) if (j < nvalid) op[j] = __float2bfloat16(f[j]);
+    }
+    if (d.out2 != nullptr) {
+      __nv_bfloat16* o2 = d.out2 + orow * d.out2_ld + lcol;
+      if (FULL) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 8)
+          *reinterpret_cast<uint4*>(o2 + j) =
+              make_uint4(pack_bf16(fmaxf(f[j], 0.f), fmaxf(f[j + 1], 0.f)), pack_bf16(fmaxf(f[j + 2], 0.f), fmaxf(f[j + 3], 0.f)),
+                         pack_bf16(fmaxf(f[j + 4], 0.f), fmaxf(f[j + 5], 0.f)), pack_bf16(fmaxf(f[j + 6], 0.f), fmaxf(f[j + 7], 0.f)));
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) if (j < nvalid) o2[j] = __float2bfloat16(fmaxf(f[j], 0.0f));
+      }
+    }
+  }
 }
 
 __global__ void __launch_bounds__(kGemmThreads, 1) pf_gemm_kernel(const __grid_constant__ GemmKernelParams P) {
@@ -189,91 +294,18 @@ __global__ void __launch_bounds__(kGemmThreads, 1) pf_gemm_kernel(const __grid_c
         uint32_t v[32];
         tmem_ld32(taddr + cb, v);
         tmem_ld_wait();
-        if (row_ok) {
-          const int ncol = c.n0 + cb;            // global N index of v[0] (selects the V^T path)
-          const int lcol = ocol0 + cb;           // logical output channel of v[0] (bias / gamma / residual index)
-          const int oc = lcol + d.out_col0;      // physical output column
-          const int nvalid = min(32, d.n_logical - lcol);   // columns of this chunk that exist
-          if (nvalid > 0) {
-            float f[32];
+        if (!row_ok) continue;
+        const int ncol = c.n0 + cb;            // global N index of v[0] (selects the V^T path)
+        const int lcol = ocol0 + cb;           // logical output channel of v[0] (bias / gamma / residual index)
+        const int nvalid = min(32, d.n_logical - lcol);   // columns of this chunk that exist
+        if (nvalid <= 0) continue;
+        float f[32];
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              float x = __uint_as_float(v[j]);
-              if (d.bias != nullptr && j < nvalid) x += __ldg(d.bias + lcol + j);
-              f[j] = apply_act(x, d.act);
-            }
-            if (d.res1 != nullptr) {
-              const __nv_bfloat16* rp = d.res1 + orow * d.res_ld + lcol;
-#pragma unroll
-              for (int j = 0; j < 32; ++j) if (j < nvalid) f[j] += __bfloat162float(rp[j]);
-            }
-            if (d.res2 != nullptr) {
-              const __nv_bfloat16* rp = d.res2 + orow * d.res_ld + lcol;
-#pragma unroll
-              for (int j = 0; j < 32; ++j) if (j < nvalid) f[j] += __bfloat162float(rp[j]);
-            }
-            if (d.vt != nullptr && ncol >= d.vt_col0) {
-              // attention V written transposed: vt[(b*heads + h)*64 + dd][token]
-              int m = static_cast<int>(orow);
-              int b = m / d.vt_seq, tok = m - b * d.vt_seq;
-#pragma unroll
-              for (int j = 0; j < 32; ++j) {
-                int cc = ncol + j - d.vt_col0;      // h*64 + dd
-                if (j < nvalid)
-                  d.vt[(static_cast<long long>(b) * d.vt_dim + cc) * d.vt_seq_pad + tok] = __float2bfloat16(f[j]);
-              }
-            } else if (d.gamma != nullptr) {
-              // x <- x + gamma * (acc + bias): fp32 residual stream updated in place
-              float* xp = reinterpret_cast<float*>(d.out) + orow * d.out_ld + oc;
-              if (nvalid == 32) {
-#pragma unroll
-                for (int j = 0; j < 32; j += 4) {
-                  float4 xv = *reinterpret_cast<float4*>(xp + j);
-                  float4 g = __ldg(reinterpret_cast<const float4*>(d.gamma + lcol + j));
-                  xv.x += g.x * f[j]; xv.y += g.y * f[j + 1]; xv.z += g.z * f[j + 2]; xv.w += g.w * f[j + 3];
-                  *reinterpret_cast<float4*>(xp + j) = xv;
-                }
-              } else {
-                for (int j = 0; j < nvalid; ++j) xp[j] += __ldg(d.gamma + lcol + j) * f[j];
-              }
-            } else if (d.out_f32) {
-              float* op = reinterpret_cast<float*>(d.out) + orow * d.out_ld + oc;
-              if (nvalid == 32) {
-#pragma unroll
-                for (int j = 0; j < 32; j += 4)
-                  *reinterpret_cast<float4*>(op + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
-              } else {
-                for (int j = 0; j < nvalid; ++j) op[j] = f[j];
-              }
-            } else {
-              __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(d.out) + orow * d.out_ld + oc;
-              if (nvalid == 32) {
-#pragma unroll
-                for (int j = 0; j < 32; j += 8) {
-                  uint4 pk = make_uint4(pack_bf16(f[j], f[j + 1]), pack_bf16(f[j + 2], f[j + 3]),
-                                        pack_bf16(f[j + 4], f[j + 5]), pack_bf16(f[j + 6], f[j + 7]));
-                  *reinterpret_cast<uint4*>(op + j) = pk;
-                }
-              } else {
-                for (int j = 0; j < nvalid; ++j) op[j] = __float2bfloat16(f[j]);
-              }
-              if (d.out2 != nullptr) {
-                __nv_bfloat16* o2 = d.out2 + orow * d.out2_ld + lcol;
-                if (nvalid == 32) {
-#pragma unroll
-                  for (int j = 0; j < 32; j += 8) {
-                    uint4 pk = make_uint4(pack_bf16(fmaxf(f[j], 0.f), fmaxf(f[j + 1], 0.f)),
-                                          pack_bf16(fmaxf(f[j + 2], 0.f), fmaxf(f[j + 3], 0.f)),
-                                          pack_bf16(fmaxf(f[j + 4], 0.f), fmaxf(f[j + 5], 0.f)),
-                                          pack_bf16(fmaxf(f[j + 6], 0.f), fmaxf(f[j + 7], 0.f)));
-                    *reinterpret_cast<uint4*>(o2 + j) = pk;
-                  }
-                } else {
-                  for (int j = 0; j < nvalid; ++j) o2[j] = __float2bfloat16(fmaxf(f[j], 0.0f));
-                }
-              }
-            }
-          }
+        for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+        if (nvalid == 32) {
+          epilogue_chunk<true>(d, f, orow, ncol, lcol, 32);
+        } else {
+          epilogue_chunk<false>(d, f, orow, ncol, lcol, nvalid);
         }
       }
       tc_fence_before();

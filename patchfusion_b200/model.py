@@ -6,6 +6,7 @@ image_hr, tile_cfg, cai_mode, process_num)` contract and error behaviour as refe
 libpf_b200 (sm_100a) through `Engine`.  There is no CPU path: calling forward on CPU tensors raises.
 """
 import math
+import os
 import random
 
 import numpy as np
@@ -109,6 +110,10 @@ class PatchFusion(ParamTree, PyTorchModelHubMixin):
         self._build_tree(state_layout(config))      # raises ValueError / NotImplementedError like the reference
         self.consistency_training = False
         self._engine = None
+        self._graphs = {}
+        self.graph_launches = 0
+        self._coarse = None
+        self.use_cuda_graphs = os.environ.get('PF_B200_GRAPHS', '1') != '0'
         self._mask_cache = {}
         if config.load_branch:
             for which, path in zip(('coarse_branch', 'fine_branch'), config.pretrain_model):
@@ -147,11 +152,11 @@ class PatchFusion(ParamTree, PyTorchModelHubMixin):
         return {k: v for k, v in self.state_dict().items() if 'coarse_branch' not in k and 'fine_branch' not in k}
 
     def load_state_dict(self, *a, **kw):
-        self._engine = None
+        self._engine, self._graphs = None, {}
         return super().load_state_dict(*a, **kw)
 
     def _apply(self, fn, *a, **kw):
-        self._engine = None
+        self._engine, self._graphs = None, {}
         return super()._apply(fn, *a, **kw)
 
     def init_synthetic_weights(self, seed=0):
@@ -205,29 +210,65 @@ class PatchFusion(ParamTree, PyTorchModelHubMixin):
         return d[:, None].clone(), [self._nchw(f) for f in feats]
 
     # ------------------------------------------------------------------ tiling
-    def _tile_batch(self, eng, image_hr, raw_origins, coarse, tile_cfg, process_num):
-        """Fused depth for tiles at raw (y, x) origins: yields (fp32 [p, ph, pw] buffer, p) per micro-batch; the
-        buffer is reused by the next micro-batch, so consume it (stitch) before advancing."""
+    def _graphed(self, key, fn):
+        """Run `fn` (a fixed kernel sequence over static buffers) through a CUDA graph: first call runs eagerly
+        (allocating the engine buffers and caching the TMA maps) and captures, later calls replay.  One graph per
+        (stage, micro-batch size, geometry): ~900 launches per micro-batch collapse into one host call."""
+        from . import lib
+        if not self.use_cuda_graphs or lib.PROFILER is not None:
+            return fn()
+        ent = self._graphs.get(key)
+        if ent is None:
+            fn()
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            n0 = lib.launch_count()
+            with torch.cuda.graph(g):
+                fn()
+            self._graphs[key] = (g, lib.launch_count() - n0)
+            return None
+        ent[0].replay()
+        self.graph_launches += ent[1]          # kernels executed by the replay (for bench.py's gpu_launches)
+        return None
+
+    def _coarse_stage(self, eng, lr):
+        cd, cf = eng.branch('coarse', lr)
+        self._coarse = (cd[0], cf, eng.g2l(cf))
+
+    def _tiles_stage(self, eng, img, T, geom, canvas, mask, up):
+        """crop+resize -> fine branch -> fusion -> scatter-stitch for one micro-batch of T tiles whose origins/boxes
+        sit in the static device buffers of `self._tile_io(T)`."""
         from . import ops
-        cd, cf, g2l = coarse
-        dev = image_hr.device
-        H, W = tile_cfg['image_raw_shape']
-        h, w = tile_cfg['patch_raw_shape']
-        ph, pw = self.patch_process_shape
+        H, W, h, w, ph, pw = geom
+        num, den, CH, CW = canvas
+        io = self._tile_io(eng, T)
+        cd, cf, g2l = self._coarse
+        crops = eng.buf('tile.crops', (T, 3, ph, pw), torch.float32)
+        ops.call('pf_crop_resize', img, H, W, io['raw'], T, h, w, ph, pw, crops, ops.stream_ptr())
+        fd, ff = eng.branch('fine', crops)
+        pred = eng.fusion(crops, io['boxes'], fd, ff, cd, cf, g2l)
+        ops.call('pf_stitch_accumulate', num, den, CH, CW, pred, T, ph, pw, io['dst'], mask, up[0], up[1],
+                 ops.stream_ptr())
+
+    def _tile_io(self, eng, T):
+        return dict(raw=eng.buf('tile.raw', (T, 2), torch.int32), dst=eng.buf('tile.dst', (T, 2), torch.int32),
+                    boxes=eng.buf('tile.boxes', (T, 4), torch.float32))
+
+    def _run_tiles(self, eng, img, raw, dst, geom, canvas, mask, up, process_num):
+        H, W, h, w, ph, pw = geom
         fx = np.float32(1 / W * pw)
         fy = np.float32(1 / H * ph)
-        for s in range(0, len(raw_origins), process_num):
-            chunk = raw_origins[s:s + process_num]
-            T = len(chunk)
-            org = torch.tensor(chunk, dtype=torch.int32, device=dev)
+        for s in range(0, len(raw), process_num):
+            chunk, T = raw[s:s + process_num], len(raw[s:s + process_num])
+            io = self._tile_io(eng, T)
+            io['raw'].copy_(torch.tensor(chunk, dtype=torch.int32))
+            io['dst'].copy_(torch.tensor(dst[s:s + T], dtype=torch.int32))
+            # boxes exactly as baseline_pretrain.py:268-282: int pixel box * fp32 factor
             bx = np.array([[np.float32(x) * fx, np.float32(y) * fy, np.float32(x + w) * fx, np.float32(y + h) * fy]
                            for (y, x) in chunk], dtype=np.float32)
-            boxes = torch.tensor(bx, device=dev)
-            crops = eng.buf('tile.crops', (T, 3, ph, pw), torch.float32)
-            ops.call('pf_crop_resize', image_hr, H, W, org, T, h, w, ph, pw, crops, ops.stream_ptr())
-            fd, ff = eng.branch('fine', crops)
-            pred = eng.fusion(crops, boxes, fd, ff, cd, cf, g2l)
-            yield pred, T
+            io['boxes'].copy_(torch.from_numpy(bx))
+            self._graphed(('tiles', T) + tuple(geom) + (canvas[2], canvas[3]) + tuple(up),
+                          lambda: self._tiles_stage(eng, img, T, geom, canvas, mask, up))
 
     @torch.no_grad()
     def forward(self, mode, image_lr, image_hr, depth_gt=None, crops_image_hr=None, crop_depths=None, bboxs=None,
@@ -243,21 +284,24 @@ class PatchFusion(ParamTree, PyTorchModelHubMixin):
         eng = self.engine()
         dev = image_hr.device
         st = ops.stream_ptr
-        img = image_hr[0].float().contiguous()
         H, W = tile_cfg['image_raw_shape']
-        assert tuple(img.shape[-2:]) == (H, W), 'image_hr must already be at image_raw_shape'
+        assert tuple(image_hr.shape[-2:]) == (H, W), 'image_hr must already be at image_raw_shape'
         h, w = tile_cfg['patch_raw_shape']
         ph, pw = self.patch_process_shape
         RH, RW = tile_cfg['patch_reensemble_shape']
+        geom = (H, W, h, w, ph, pw)
+        # inputs into static buffers (stable addresses for the captured graphs)
+        img = eng.buf('in.image_hr', (3, H, W), torch.float32)
+        img.copy_(image_hr[0])
+        lr = eng.buf('in.image_lr', (1, 3, ph, pw), torch.float32)
+        lr.copy_(image_lr)
 
-        cd, cf = eng.branch('coarse', image_lr.float().contiguous())
-        cd = cd[0].clone()
-        cf = [type(f)(f.t.clone(), f.C) for f in cf]       # coarse maps outlive the fine branch's buffer reuse
-        g2l = eng.g2l(cf)
-        coarse = (cd, cf, g2l)
+        self._graphed(('coarse', ph, pw), lambda: self._coarse_stage(eng, lr))
 
-        num = torch.zeros((RH, RW), dtype=torch.float32, device=dev)
-        den = torch.zeros((RH, RW), dtype=torch.float32, device=dev)
+        num = eng.buf('canvas.num', (RH, RW), torch.float32)
+        den = eng.buf('canvas.den', (RH, RW), torch.float32)
+        num.zero_()
+        den.zero_()
         mask = self._mask((ph, pw), dev)
         offsets = [((0, 0), (0, 0))]
         if cai_mode == 'm2' or cai_mode[0] == 'r':
@@ -270,24 +314,18 @@ class PatchFusion(ParamTree, PyTorchModelHubMixin):
             ny, nx = (H - oy) // h, (W - ox) // w
             raw += [(h * a + oy, w * b + ox) for a in range(ny) for b in range(nx)]
             proc += [(ph * a + py, pw * b + px) for a in range(ny) for b in range(nx)]
-        done = 0
-        for pred, T in self._tile_batch(eng, img, raw, coarse, tile_cfg, process_num):
-            org = torch.tensor(proc[done:done + T], dtype=torch.int32, device=dev)
-            ops.call('pf_stitch_accumulate', num, den, RH, RW, pred, T, ph, pw, org, mask, 0, 0, st())
-            done += T
+        self._run_tiles(eng, img, raw, proc, geom, (num, den, RH, RW), mask, (0, 0), process_num)
         if cai_mode[0] == 'r':
             mask = self._mask((h, w), dev)
-            n2 = torch.zeros((H, W), dtype=torch.float32, device=dev)
-            d2 = torch.zeros((H, W), dtype=torch.float32, device=dev)
+            n2 = eng.buf('canvas.num_raw', (H, W), torch.float32)
+            d2 = eng.buf('canvas.den_raw', (H, W), torch.float32)
             ops.call('pf_stitch_resize', num, den, RH, RW, H, W, n2, d2, st())
             num, den = n2, d2
             for _ in range(int(cai_mode[1:]) // process_num):
                 ys = [random.randint(0, H - h - 1) for _ in range(process_num)]     # baseline_pretrain.py:155-156
                 x0 = random.randint(0, W - w - 1)
                 raw = [(y, x0) for y in ys]
-                for pred, T in self._tile_batch(eng, img, raw, coarse, tile_cfg, process_num):
-                    org = torch.tensor(raw, dtype=torch.int32, device=dev)
-                    ops.call('pf_stitch_accumulate', num, den, H, W, pred, T, ph, pw, org, mask, h, w, st())
+                self._run_tiles(eng, img, raw, raw, geom, (num, den, H, W), mask, (h, w), process_num)
         out = torch.empty_like(num)
         ops.call('pf_stitch_finalize', num, den, ops.C.c_int64(num.numel()), out, st())
         depth = out[None, None]

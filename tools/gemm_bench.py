@@ -50,12 +50,18 @@ for name, kind, p in SHAPES:
         flops = 2.0 * NB * H * W * sum(cs) * taps * N
     for _ in range(3):
         fn()
+    torch.cuda.synchronize()
+    REP = 10
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        for _ in range(REP):
+            fn()
     ts = []
     for _ in range(5):
         flush.zero_()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(); fn(); e1.record(); torch.cuda.synchronize()
-        ts.append(e0.elapsed_time(e1))
+        e0.record(); g.replay(); e1.record(); torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1) / REP)
     ms = sorted(ts)[len(ts) // 2]
     d = fn()
     print('%-46s %8.3f ms %8.1f TF/s  (block_n %d, m_tiles %d, n_tiles %d)' % (name, ms, flops / ms / 1e9, d.block_n, d.m_tiles, d.n_tiles), flush=True)
