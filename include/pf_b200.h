@@ -67,6 +67,10 @@ typedef struct pf_gemm_desc {
   void* out2; int32_t out2_ld;                           /* optional second bf16 output = relu(v) */
   int32_t ps, ps_cout;                                   /* ConvTranspose k==s as GEMM + pixel shuffle (ps = k) */
   void* vt; int32_t vt_col0, vt_seq, vt_seq_pad, vt_dim; /* attention V columns written transposed */
+  /* fused trailing 1x1 layer on the activated row (e.g. the 80->4 / 128->nA / 32->1 heads): out3[row, i] =
+   * act2(b2[i] + sum_j w2[i*N + j] * v[j]), i < n2 <= 16; needs N <= block_n (one N tile).  skip_main != 0
+   * suppresses the main store. */
+  const float* w2; const float* b2; int32_t n2, act2, skip_main; float* out3; int32_t out3_ld;
 } pf_gemm_desc;
 
 int pf_gemm(pf_gemm_desc* desc, void* stream);

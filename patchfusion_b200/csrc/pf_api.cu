@@ -2,6 +2,7 @@
 #include <cuda_bf16.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <atomic>
@@ -256,7 +257,18 @@ int pf_gemm(pf_gemm_desc* u, void* stream) {
   u->block_n = bn; u->n_tiles = d.n_tiles;
   d.M = u->M; d.NB = u->NB; d.H = u->H; d.W = u->W;
   CUtensorMap tmA[3], tmB;
-  if (u->a_mode == 1) {
+  // 3x3 convs go through the halo-tile kernel (one A fetch per 64-channel chunk instead of nine) unless the caller
+  // pins a tile shape or PF_B200_NO_HALO is set.
+  static const bool no_halo = getenv("PF_B200_NO_HALO") != nullptr;
+  const bool halo = u->a_mode == 1 && u->taps == 9 && u->bh == 0 && u->bw == 0 && !no_halo;
+  d.halo = halo ? 1 : 0;
+  if (halo) {
+    d.bh = 16; d.bw = 8;
+    d.tiles_y = (u->H + 15) / 16; d.tiles_x = (u->W + 7) / 8;
+    d.m_tiles = u->NB * d.tiles_y * d.tiles_x;
+    for (int s = 0; s < u->num_src; ++s)
+      if (tmap_4d_nhwc_bf16(&tmA[s], u->a_ptr[s], u->a_c[s], u->W, u->H, u->NB, u->a_ld[s], 64, 10, 18)) return 1;
+  } else if (u->a_mode == 1) {
     int bh = u->bh, bw = u->bw;
     if (bh == 0 || bw == 0) choose_tile(u->H, u->W, &bh, &bw);
     if (bh * bw != 128) return set_error("pf_gemm: bh*bw must be 128");
@@ -289,6 +301,13 @@ int pf_gemm(pf_gemm_desc* u, void* stream) {
     if (u->N != d.ps * d.ps * cpad) return set_error("pf_gemm: pixel shuffle N %d != k*k*pad32(Cout) %d", u->N, d.ps * d.ps * cpad);
     d.ps_cout_pad = cpad;
     d.n_logical = u->ps_cout;
+  }
+  d.w2 = u->w2; d.b2 = u->b2; d.n2 = u->n2; d.act2 = u->act2; d.skip_main = u->skip_main;
+  d.out3 = u->out3; d.out3_ld = u->out3_ld;
+  if (d.w2) {
+    if (d.n_tiles != 1) return set_error("pf_gemm: fused trailing layer needs the whole row in one N tile (N %d)", u->N);
+    if (d.n2 < 1 || d.n2 > 16 || !d.out3) return set_error("pf_gemm: fused trailing layer n2 %d (1..16), out3 required", d.n2);
+    if (u->N % 4) return set_error("pf_gemm: fused trailing layer needs N % 4 == 0");
   }
   d.vt = static_cast<__nv_bfloat16*>(u->vt);
   d.vt_col0 = u->vt_col0; d.vt_seq = u->vt_seq; d.vt_seq_pad = u->vt_seq_pad; d.vt_dim = u->vt_dim;

@@ -64,9 +64,11 @@ __device__ __forceinline__ TileCoord decode_tile(const GemmDesc& d, int t) {
 // One 32-column chunk of one accumulator row: bias -> activation -> residuals -> store.  FULL == all 32 columns exist
 // (vector loads/stores, no predication); the tail variant predicates every column but keeps all indices static so
 // f[] stays in registers.
+constexpr int kMaxTail = 16;   // widest fused trailing 1x1 layer
+
 template <bool FULL>
 __device__ __forceinline__ void epilogue_chunk(const GemmDesc& d, float (&f)[32], long long orow, int ncol, int lcol,
-                                               int nvalid) {
+                                               int nvalid, float (&y2)[kMaxTail]) {
   if (d.bias != nullptr) {
     if (FULL) {
       const float4* bp = reinterpret_cast<const float4*>(d.bias + lcol);
@@ -85,10 +87,33 @@ __device__ __forceinline__ void epilogue_chunk(const GemmDesc& d, float (&f)[32]
     for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.0f);
   } else if (d.act == PF_ACT_GELU) {
 #pragma unroll
-    for (int j = 0; j < 32; ++j) f[j] = gelu_erf(f[j]);
+    for (int j = 0; j < 32; ++j) if (FULL || j < nvalid) f[j] = gelu_erf(f[j]);
   } else if (d.act == PF_ACT_SOFTPLUS) {
 #pragma unroll
-    for (int j = 0; j < 32; ++j) f[j] = softplus(f[j]);
+    for (int j = 0; j < 32; ++j) if (FULL || j < nvalid) f[j] = softplus(f[j]);
+  }
+  // fused trailing 1x1 layer: y[i] += sum_j W2[i][lcol + j] * f[j]  (row-local: the thread owns the whole row)
+  if (d.w2 != nullptr) {
+#pragma unroll
+    for (int i = 0; i < kMaxTail; ++i) {
+      if (i < d.n2) {
+        const float* wp = d.w2 + static_cast<long long>(i) * d.n_logical + lcol;
+        float a = 0.f;
+        if (FULL) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float4 w4 = __ldg(reinterpret_cast<const float4*>(wp) + j);
+            a = fmaf(w4.x, f[4 * j], a); a = fmaf(w4.y, f[4 * j + 1], a);
+            a = fmaf(w4.z, f[4 * j + 2], a); a = fmaf(w4.w, f[4 * j + 3], a);
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) if (j < nvalid) a = fmaf(__ldg(wp + j), f[j], a);
+        }
+        y2[i] += a;
+      }
+    }
+    if (d.skip_main) return;
   }
 #pragma unroll
   for (int rsel = 0; rsel < 2; ++rsel) {
@@ -169,6 +194,83 @@ __device__ __forceinline__ void epilogue_chunk(const GemmDesc& d, float (&f)[32]
         for (int j = 0; j < 32; ++j) if (j < nvalid) o2[j] = __float2bfloat16(fmaxf(f[j], 0.0f));
       }
     }
+  }
+}
+
+// Epilogue warps (4 warps, TMEM lane quadrant = warp & 3): drain accumulator stage `acc` of each tile this CTA owns.
+__device__ __forceinline__ void epilogue_loop(const GemmDesc& d, int total_tiles, uint64_t* tmem_full,
+                                              uint64_t* tmem_empty, uint32_t tmem_base, int warp, int lane) {
+  const int q = warp & 3;                 // TMEM lane quadrant this warp may access
+  const int r = q * 32 + lane;            // accumulator row owned by this thread
+  int acc = 0; uint32_t acc_phase = 0;
+  for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+    TileCoord c = decode_tile(d, t);
+    // ---- row mapping
+    bool row_ok;
+    long long orow;       // output row (pixel / token) index
+    if (d.a_mode == 1) {
+      int yy = r / d.bw, xx = r - yy * d.bw;
+      int y = c.y0 + yy, x = c.x0 + xx;
+      row_ok = (y < d.H) && (x < d.W);
+      orow = (static_cast<long long>(c.img) * d.H + y) * d.W + x;
+    } else {
+      int m = c.m0 + r;
+      row_ok = m < d.M;
+      orow = m;
+    }
+    int ocol0 = c.n0;     // output column of accumulator column 0
+    if (d.ps > 1 && d.a_mode == 0) {
+      // ConvTranspose k==s: columns are ordered (ky, kx, cout); this N tile belongs to one (ky,kx).
+      int tap = c.n0 / d.ps_cout_pad;
+      ocol0 = c.n0 - tap * d.ps_cout_pad;
+      int ky = tap / d.ps, kx = tap - ky * d.ps;
+      int m = c.m0 + r;
+      int img = m / (d.H * d.W);
+      int rem = m - img * d.H * d.W;
+      int y = rem / d.W, x = rem - y * d.W;
+      orow = (static_cast<long long>(img) * d.H * d.ps + y * d.ps + ky) * (d.W * d.ps) + x * d.ps + kx;
+    }
+    mbar_wait(&tmem_full[acc], acc_phase);
+    tc_fence_after();
+    const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * d.block_n;
+    float y2[kMaxTail];
+#pragma unroll
+    for (int i = 0; i < kMaxTail; ++i) y2[i] = 0.f;
+    for (int cb = 0; cb < d.block_n; cb += 32) {
+      uint32_t v[32];
+      tmem_ld32(taddr + cb, v);
+      tmem_ld_wait();
+      if (!row_ok) continue;
+      const int ncol = c.n0 + cb;            // global N index of v[0] (selects the V^T path)
+      const int lcol = ocol0 + cb;           // logical output channel of v[0] (bias / gamma / residual index)
+      const int nvalid = min(32, d.n_logical - lcol);   // columns of this chunk that exist
+      if (nvalid <= 0) continue;
+      float f[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+      if (nvalid == 32) {
+        epilogue_chunk<true>(d, f, orow, ncol, lcol, 32, y2);
+      } else {
+        epilogue_chunk<false>(d, f, orow, ncol, lcol, nvalid, y2);
+      }
+    }
+    if (d.w2 != nullptr && row_ok) {
+      // trailing layer output: fp32 [rows, out3_ld], bias + activation
+      float* op = d.out3 + orow * d.out3_ld;
+#pragma unroll
+      for (int i = 0; i < kMaxTail; ++i) {
+        if (i < d.n2) {
+          float v2 = y2[i] + (d.b2 != nullptr ? __ldg(d.b2 + i) : 0.f);
+          if (d.act2 == PF_ACT_RELU) v2 = fmaxf(v2, 0.f);
+          else if (d.act2 == PF_ACT_SOFTPLUS) v2 = softplus(v2);
+          else if (d.act2 == PF_ACT_GELU) v2 = gelu_erf(v2);
+          op[i] = v2;
+        }
+      }
+    }
+    tc_fence_before();
+    mbar_arrive(&tmem_empty[acc]);
+    if (++acc == 2) { acc = 0; acc_phase ^= 1; }
   }
 }
 
@@ -257,63 +359,134 @@ __global__ void __launch_bounds__(kGemmThreads, 1) pf_gemm_kernel(const __grid_c
     }
   } else {
     // ===================== epilogue (warps 2..5) =====================
-    const int q = warp & 3;                 // TMEM lane quadrant this warp may access
-    const int r = q * 32 + lane;            // accumulator row owned by this thread
-    int acc = 0; uint32_t acc_phase = 0;
-    for (int t = blockIdx.x; t < P.total_tiles; t += gridDim.x) {
-      TileCoord c = decode_tile(d, t);
-      // ---- row mapping
-      bool row_ok;
-      long long orow;       // output row (pixel / token) index
-      if (d.a_mode == 1) {
-        int yy = r / d.bw, xx = r - yy * d.bw;
-        int y = c.y0 + yy, x = c.x0 + xx;
-        row_ok = (y < d.H) && (x < d.W);
-        orow = (static_cast<long long>(c.img) * d.H + y) * d.W + x;
-      } else {
-        int m = c.m0 + r;
-        row_ok = m < d.M;
-        orow = m;
-      }
-      int ocol0 = c.n0;     // output column of accumulator column 0
-      if (d.ps > 1 && d.a_mode == 0) {
-        // ConvTranspose k==s: columns are ordered (ky, kx, cout); this N tile belongs to one (ky,kx).
-        int tap = c.n0 / d.ps_cout_pad;
-        ocol0 = c.n0 - tap * d.ps_cout_pad;
-        int ky = tap / d.ps, kx = tap - ky * d.ps;
-        int m = c.m0 + r;
-        int img = m / (d.H * d.W);
-        int rem = m - img * d.H * d.W;
-        int y = rem / d.W, x = rem - y * d.W;
-        orow = (static_cast<long long>(img) * d.H * d.ps + y * d.ps + ky) * (d.W * d.ps) + x * d.ps + kx;
-      }
-      mbar_wait(&tmem_full[acc], acc_phase);
-      tc_fence_after();
-      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * d.block_n;
-      for (int cb = 0; cb < d.block_n; cb += 32) {
-        uint32_t v[32];
-        tmem_ld32(taddr + cb, v);
-        tmem_ld_wait();
-        if (!row_ok) continue;
-        const int ncol = c.n0 + cb;            // global N index of v[0] (selects the V^T path)
-        const int lcol = ocol0 + cb;           // logical output channel of v[0] (bias / gamma / residual index)
-        const int nvalid = min(32, d.n_logical - lcol);   // columns of this chunk that exist
-        if (nvalid <= 0) continue;
-        float f[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-        if (nvalid == 32) {
-          epilogue_chunk<true>(d, f, orow, ncol, lcol, 32);
-        } else {
-          epilogue_chunk<false>(d, f, orow, ncol, lcol, nvalid);
-        }
-      }
-      tc_fence_before();
-      mbar_arrive(&tmem_empty[acc]);
-      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
-    }
+    epilogue_loop(d, P.total_tiles, tmem_full, tmem_empty, tmem_base, warp, lane);
   }
 
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// 3x3 convolution with a shared-memory HALO tile (stride 1, zero pad 1).
+//
+// The generic kernel above fetches the A operand once per tap: 9 TMA boxes of 16 KB per 64-channel chunk, all hitting
+// the same pixels.  Here one TMA box {64 ch, 10, 18, 1} brings the (16+2) x (8+2) pixel neighbourhood of a 16x8
+// output tile (23 KB) and all nine taps are issued from it: for tap (dy,dx) the 128 accumulator rows are the 16
+// image rows of 8 pixels starting at halo row (dy*10 + dx), i.e. a K-major SWIZZLE_128B operand whose 8-row groups
+// are 1280 B apart - expressed purely through the UMMA descriptor's start address and stride-byte-offset (the
+// 128B-swizzle XOR is a function of the shared-memory address bits, so 128-B-granular shifted views of a TMA-written
+// tile stay consistent).  A traffic from L2 drops 6.3x; the weights stream per (chunk, tap) as before.
+// Warp roles and the TMEM double-buffered epilogue are those of pf_gemm_kernel.
+constexpr int kHaloW = 10, kHaloH = 18;
+constexpr int kHaloBytes = kHaloW * kHaloH * 128;          // 23040
+constexpr int kHaloSlot = 24 * 1024;                        // 1024-B aligned slot
+constexpr int kHaloSlots = 3;
+
+__global__ void __launch_bounds__(kGemmThreads, 1) pf_conv3_halo_kernel(const __grid_constant__ GemmKernelParams P) {
+  extern __shared__ uint8_t smem_raw[];
+  const GemmDesc& d = P.d;
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int stages = P.stages;                              // B ring
+  const int b_tile_bytes = d.block_n * kBlockK * 2;
+  uint8_t* smem_b = smem + kHaloSlots * kHaloSlot;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_b + stages * b_tile_bytes);
+  uint64_t* a_full = bars;                                  // [kHaloSlots]
+  uint64_t* a_empty = a_full + kHaloSlots;
+  uint64_t* b_full = a_empty + kHaloSlots;                  // [stages]
+  uint64_t* b_empty = b_full + stages;
+  uint64_t* tmem_full = b_empty + stages;                   // [2]
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < d.num_src; ++s) prefetch_tmap(&P.tmA[s]);
+    prefetch_tmap(&P.tmB);
+    for (int s = 0; s < kHaloSlots; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
+    for (int s = 0; s < stages; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], 128); }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int as = 0; uint32_t aph = 0;
+      int bs = 0; uint32_t bph = 0;
+      for (int t = blockIdx.x; t < P.total_tiles; t += gridDim.x) {
+        TileCoord c = decode_tile(d, t);
+        int kbase = 0;                                       // first 64-wide K block of this source in the weights
+        for (int s = 0; s < d.num_src; ++s) {
+          const int nch = d.chunks[s];
+          for (int ch = 0; ch < nch; ++ch) {
+            mbar_wait(&a_empty[as], aph ^ 1);
+            mbar_expect_tx(&a_full[as], kHaloBytes);
+            tma_load_4d(smem + as * kHaloSlot, &P.tmA[s], &a_full[as], ch * kBlockK, c.x0 - 1, c.y0 - 1, c.img);
+            if (++as == kHaloSlots) { as = 0; aph ^= 1; }
+            for (int tap = 0; tap < 9; ++tap) {
+              mbar_wait(&b_empty[bs], bph ^ 1);
+              mbar_expect_tx(&b_full[bs], b_tile_bytes);
+              tma_load_2d(smem_b + bs * b_tile_bytes, &P.tmB, &b_full[bs], (kbase + tap * nch + ch) * kBlockK, c.n0);
+              if (++bs == stages) { bs = 0; bph ^= 1; }
+            }
+          }
+          kbase += 9 * nch;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc_bf16(kBlockM, d.block_n);
+      int as = 0; uint32_t aph = 0;
+      int bs = 0; uint32_t bph = 0;
+      int acc = 0; uint32_t acc_phase = 0;
+      for (int t = blockIdx.x; t < P.total_tiles; t += gridDim.x) {
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + acc * d.block_n;
+        uint32_t first = 1;
+        for (int s = 0; s < d.num_src; ++s) {
+          for (int ch = 0; ch < d.chunks[s]; ++ch) {
+            mbar_wait(&a_full[as], aph);
+            tc_fence_after();
+            const uint32_t halo = smem_u32(smem + as * kHaloSlot);
+#pragma unroll 1
+            for (int tap = 0; tap < 9; ++tap) {
+              const int dy = tap / 3, dx = tap - dy * 3;
+              mbar_wait(&b_full[bs], bph);
+              tc_fence_after();
+              // A view: rows (dy*10 + dx) + 10*g + i, g = image row of the tile, i = pixel within the 8-wide row
+              uint64_t adesc = umma_desc_k128(halo + (dy * kHaloW + dx) * 128);
+              adesc = (adesc & ~(static_cast<uint64_t>(0x3FFF) << 32)) | (static_cast<uint64_t>((kHaloW * 128) >> 4) << 32);
+              const uint64_t bdesc = umma_desc_k128(smem_u32(smem_b + bs * b_tile_bytes));
+#pragma unroll
+              for (int k = 0; k < kBlockK / 16; ++k) {
+                umma_bf16(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, first ? 0u : 1u);
+                first = 0;
+              }
+              umma_commit(&b_empty[bs]);
+              if (++bs == stages) { bs = 0; bph ^= 1; }
+            }
+            umma_commit(&a_empty[as]);                       // halo slot reusable once its 36 MMAs retire
+            if (++as == kHaloSlots) { as = 0; aph ^= 1; }
+          }
+        }
+        umma_commit(&tmem_full[acc]);
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else {
+    epilogue_loop(d, P.total_tiles, tmem_full, tmem_empty, tmem_base, warp, lane);
+  }
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
@@ -357,7 +530,24 @@ int gemm_launch(const GemmDesc& d, const CUtensorMap* tmA, const CUtensorMap& tm
   if (P.total_tiles <= 0 || ks <= 0) return set_error("gemm: empty problem");
   int grid = P.total_tiles < g_sm_count ? P.total_tiles : g_sm_count;
   size_t smem = 1024 + static_cast<size_t>(stages) * stage_bytes + 256;
-  pf_gemm_kernel<<<grid, kGemmThreads, smem, stream>>>(P);
+  if (d.halo) {
+    static bool halo_attr = false;
+    if (!halo_attr) {
+      cudaError_t e2 = cudaFuncSetAttribute(pf_conv3_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
+      if (e2 != cudaSuccess) return set_error("cudaFuncSetAttribute(pf_conv3_halo_kernel): %s", cudaGetErrorString(e2));
+      halo_attr = true;
+    }
+    int b_bytes = d.block_n * kBlockK * 2;
+    int hb = kMaxSmem - 1024 - 512 - kHaloSlots * kHaloSlot;
+    int hstages = hb / b_bytes;
+    if (hstages > 8) hstages = 8;
+    if (hstages < 2) return set_error("conv3 halo: not enough shared memory");
+    P.stages = hstages;
+    size_t hsmem = 1024 + static_cast<size_t>(kHaloSlots) * kHaloSlot + static_cast<size_t>(hstages) * b_bytes + 512;
+    pf_conv3_halo_kernel<<<grid, kGemmThreads, hsmem, stream>>>(P);
+  } else {
+    pf_gemm_kernel<<<grid, kGemmThreads, smem, stream>>>(P);
+  }
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_error("pf_gemm_kernel launch: %s", cudaGetErrorString(e));
   count_launch();

@@ -10,6 +10,7 @@ namespace pf {
 // Kernel-side view of pf_gemm_desc (device pointers typed, host-only fields dropped).
 struct GemmDesc {
   int num_src, a_mode, taps;
+  int halo;              // 3x3 conv through the halo-tile kernel (bh=16, bw=8)
   int chunks[3];
   int M, NB, H, W, bh, bw, tiles_y, tiles_x, m_tiles;
   int N, block_n, n_tiles;
@@ -27,6 +28,12 @@ struct GemmDesc {
   int n_logical;         // logical output channels (N, or Cout for pixel shuffle)
   __nv_bfloat16* vt;
   int vt_col0, vt_seq, vt_seq_pad, vt_dim;
+  // fused trailing 1x1 layer (n2 <= 16 outputs per row, whole row in one N tile)
+  const float* w2;
+  const float* b2;
+  int n2, act2, skip_main;
+  float* out3;
+  int out3_ld;
 };
 
 int set_error(const char* fmt, ...);

@@ -99,6 +99,10 @@ class Engine:
                  ['attractors.%d' % i for i in range(4)]:
             Wd[n + '.0'] = self._conv(pre + n + '._net.0')
             Wd[n + '.2'] = self._conv(pre + n + '._net.2')
+            w2 = self._w(pre + n + '._net.2.weight')
+            if w2.shape[0] <= 16:       # narrow second layer: fused into the first layer's epilogue (fp32 weights)
+                Wd[n + '.tail'] = (w2.reshape(w2.shape[0], -1).float().contiguous(),
+                                   self._f32(pre + n + '._net.2.bias'))
         w0 = self._w(pre + 'conditional_log_binomial.mlp.0.weight')
         b0 = self._w(pre + 'conditional_log_binomial.mlp.0.bias')
         E = hp['bin_embedding_dim']
@@ -108,6 +112,8 @@ class Engine:
         else:
             Wd['clb.0'] = ops.pack_weight(w0, b0, src_c=[32, 1, E])
         Wd['clb.2'] = self._conv(pre + 'conditional_log_binomial.mlp.2')
+        Wd['clb.tail'] = (self._w(pre + 'conditional_log_binomial.mlp.2.weight').reshape(4, -1).float().contiguous(),
+                          self._f32(pre + 'conditional_log_binomial.mlp.2.bias'))
         return Wd
 
     def _pack_branch(self, which):
@@ -162,6 +168,8 @@ class Engine:
         Wd['oc1'] = self._conv(dh + 'scratch.output_conv1')
         Wd['oc2.0'] = self._conv(dh + 'scratch.output_conv2.0')
         Wd['oc2.2'] = self._conv(dh + 'scratch.output_conv2.2')
+        Wd['oc2.tail'] = (self._w(dh + 'scratch.output_conv2.2.weight').reshape(1, -1).float().contiguous(),
+                          self._f32(dh + 'scratch.output_conv2.2.bias'))
         Wd['conv2'] = self._conv(pre + 'conv2')
         Wd['head'] = self._pack_head(pre, C, hp, drop_rel=False)
         return Wd
@@ -216,7 +224,7 @@ class Engine:
 
     # ------------------------------------------------------------------ small helpers
     def conv(self, key, pw, srcs, N=None, act=ACT_NONE, res1=None, res2=None, relu_copy=False, out=None,
-             out_dtype=BF16):
+             out_dtype=BF16, tail=None, tail_out=None, skip_main=False):
         """3x3 / 1x1 conv over NHWC maps `srcs` (list of Map) -> Map (and optionally its ReLU copy)."""
         B, (h, w) = srcs[0].B, srcs[0].hw
         N = pw.N if N is None else N
@@ -225,7 +233,8 @@ class Engine:
         o2 = Map(self.buf(key + '.relu', (B, h, w, pad_to(N, 8))), N) if relu_copy else None
         ops.gemm(pw, [s.t for s in srcs], out.t, image=(B, h, w), act=act,
                  res1=res1.t if res1 is not None else None, res2=res2.t if res2 is not None else None,
-                 out2=o2.t if o2 is not None else None, src_c=[s.C for s in srcs])
+                 out2=o2.t if o2 is not None else None, src_c=[s.C for s in srcs], tail=tail, tail_out=tail_out,
+                 skip_main=skip_main)
         return (out, o2) if relu_copy else out
 
     def resize(self, key, x, size, out=None, out_col0=0):
@@ -334,9 +343,10 @@ class Engine:
         p1 = ffb(1, p2, rn[0], rn_relu[0], (rn[0].hw[0] * 2, rn[0].hw[1] * 2))
         o = self.conv(k + 'oc1', Wd['oc1'], [p1])
         o = self.resize(k + 'oc1up', o, (H, Wimg))
-        out_conv = self.conv(k + 'oc2', Wd['oc2.0'], [o], act=ACT_RELU)
         rel = Map(self.buf(k + 'rel', (B, H, Wimg, 8), F32), 1)
-        ops.gemm(Wd['oc2.2'], [out_conv.t], rel.t, image=(B, H, Wimg), act=ACT_RELU, src_c=[out_conv.C])
+        # output_conv2: 3x3 C/2->32 + ReLU (the hooked `out_conv` tap) with the 1x1 32->1 + ReLU fused in its epilogue
+        out_conv = self.conv(k + 'oc2', Wd['oc2.0'], [o], act=ACT_RELU,
+                             tail=Wd['oc2.tail'] + (ACT_RELU,), tail_out=rel.t)
         x_d0 = self.conv(k + 'xd0', Wd['conv2'], [rn[3]])
         blocks = [p4, p3, p2, p1]
         if taps is not None:
@@ -351,8 +361,14 @@ class Engine:
         nb, E = hp['n_bins'], hp['bin_embedding_dim']
 
         def mlp(tag, name, src, act2=ACT_NONE, f32_out=False, n_out=None):
-            t = self.conv(k + tag + '.t', Wh[name + '.0'], [src], act=ACT_RELU)
             pw = Wh[name + '.2']
+            if f32_out and (name + '.tail') in Wh:
+                h, w = src.hw
+                o = Map(self.buf(k + tag + '.o', (B, h, w, pad_to(pad_to(pw.N, 8), 32)), F32), pw.N)
+                self.conv(k + tag + '.t', Wh[name + '.0'], [src], act=ACT_RELU, tail=Wh[name + '.tail'] + (act2,),
+                          tail_out=o.t, skip_main=True)
+                return o
+            t = self.conv(k + tag + '.t', Wh[name + '.0'], [src], act=ACT_RELU)
             if f32_out:
                 h, w = src.hw
                 o = Map(self.buf(k + tag + '.o', (B, h, w, pad_to(pad_to(pw.N, 8), 32)), F32), pw.N)
@@ -384,9 +400,10 @@ class Engine:
             srcs = [last, relb, emb_up]
         else:
             srcs = [last, emb_up]
-        z = self.conv(k + 'clb0', Wh['clb.0'], srcs, act=ACT_GELU)
         pt = self.buf(k + 'pt', (B, H, Wimg, 8), F32)
-        ops.gemm(Wh['clb.2'], [z.t], pt, image=(B, H, Wimg), act=ACT_SOFTPLUS, src_c=[z.C])
+        # CLB MLP: 1x1 (161->80) + GELU with the 80->4 + Softplus layer fused in its epilogue (dist_layers.py:91-98)
+        self.conv(k + 'clb0', Wh['clb.0'], srcs, act=ACT_GELU, tail=Wh['clb.tail'] + (ACT_SOFTPLUS,), tail_out=pt,
+                  skip_main=True)
         depth = self.buf(k + 'depth', (B, H, Wimg), F32)
         call('pf_logbinom_depth', pt, 8, b_t, ph, pw_, B, H, Wimg, nb, ct.c_float(_get(bcfg, 'min_temp')),
              ct.c_float(_get(bcfg, 'max_temp')), depth, st)

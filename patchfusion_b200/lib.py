@@ -35,6 +35,8 @@ class GemmDesc(C.Structure):
         ('ps', C.c_int32), ('ps_cout', C.c_int32),
         ('vt', C.c_void_p), ('vt_col0', C.c_int32), ('vt_seq', C.c_int32), ('vt_seq_pad', C.c_int32),
         ('vt_dim', C.c_int32),
+        ('w2', C.c_void_p), ('b2', C.c_void_p), ('n2', C.c_int32), ('act2', C.c_int32), ('skip_main', C.c_int32),
+        ('out3', C.c_void_p), ('out3_ld', C.c_int32),
     ]
 
 

@@ -258,8 +258,13 @@ class PatchFusion(ParamTree, PyTorchModelHubMixin):
         H, W, h, w, ph, pw = geom
         fx = np.float32(1 / W * pw)
         fy = np.float32(1 / H * ph)
-        for s in range(0, len(raw), process_num):
-            chunk, T = raw[s:s + process_num], len(raw[s:s + process_num])
+        # balanced micro-batches (e.g. 49 tiles, process_num 9 -> 9,8,8,8,8,8): at most two captured graph sizes
+        # and no ragged tail; grouping does not change any tile's result
+        nchunk = -(-len(raw) // process_num)
+        sizes = [len(raw) // nchunk + (1 if i < len(raw) % nchunk else 0) for i in range(nchunk)]
+        s = 0
+        for T in sizes:
+            chunk = raw[s:s + T]
             io = self._tile_io(eng, T)
             io['raw'].copy_(torch.tensor(chunk, dtype=torch.int32))
             io['dst'].copy_(torch.tensor(dst[s:s + T], dtype=torch.int32))
@@ -269,6 +274,7 @@ class PatchFusion(ParamTree, PyTorchModelHubMixin):
             io['boxes'].copy_(torch.from_numpy(bx))
             self._graphed(('tiles', T) + tuple(geom) + (canvas[2], canvas[3]) + tuple(up),
                           lambda: self._tiles_stage(eng, img, T, geom, canvas, mask, up))
+            s += T
 
     @torch.no_grad()
     def forward(self, mode, image_lr, image_hr, depth_gt=None, crops_image_hr=None, crop_depths=None, bboxs=None,

@@ -76,7 +76,8 @@ def pack_weight_convT(weight, bias, k):
 
 
 def gemm(pw, srcs, out, *, image=None, ps_image=None, M=None, act=ACT_NONE, res1=None, res2=None, gamma=None, out_col0=0, out2=None,
-         vt=None, vt_col0=0, vt_seq=0, vt_seq_pad=0, src_c=None, block_n=0):
+         vt=None, vt_col0=0, vt_seq=0, vt_seq_pad=0, src_c=None, block_n=0, tail=None, tail_out=None,
+         skip_main=False, tile=None):
     """srcs: list of bf16 tensors.  image=(NB,H,W) selects NHWC/conv addressing (srcs are [NB,H,W,ld]);
     otherwise srcs are [M, ld] matrices.  `out` may be bf16 or fp32; with `gamma` it is the fp32 residual stream
     updated in place (x += gamma * (acc + bias))."""
@@ -95,6 +96,8 @@ def gemm(pw, srcs, out, *, image=None, ps_image=None, M=None, act=ACT_NONE, res1
         d.a_mode = 1
         d.NB, d.H, d.W = image
         rows = d.NB * d.H * d.W
+        if tile is not None:        # pin the pixel tile (bh, bw): selects the per-tap TMA kernel for 3x3 convs
+            d.bh, d.bw = tile
     else:
         d.a_mode = 0
         d.M = M if M is not None else srcs[0].shape[0]
@@ -127,6 +130,13 @@ def gemm(pw, srcs, out, *, image=None, ps_image=None, M=None, act=ACT_NONE, res1
     if vt is not None:
         d.vt = vt.data_ptr()
         d.vt_col0, d.vt_seq, d.vt_seq_pad, d.vt_dim = vt_col0, vt_seq, vt_seq_pad, pw.N - vt_col0
+    if tail is not None:
+        # fused trailing 1x1 layer: tail = (w2 fp32 [n2, N], b2 fp32 [n2] or None, act2)
+        w2, b2, act2 = tail
+        assert w2.dtype == torch.float32 and w2.is_contiguous() and w2.shape[1] == pw.N and tail_out.dtype == torch.float32
+        d.w2, d.b2 = w2.data_ptr(), (b2.data_ptr() if b2 is not None else None)
+        d.n2, d.act2, d.skip_main = w2.shape[0], act2, 1 if skip_main else 0
+        d.out3, d.out3_ld = tail_out.data_ptr(), tail_out.shape[-1]
     if lib.PROFILER is not None:
         n_true = pw.ps_cout * pw.ps * pw.ps if pw.ps > 1 else pw.N
         lib.PROFILER.next_flops = 2.0 * rows * sum(cs) * pw.taps * n_true

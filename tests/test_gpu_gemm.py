@@ -77,7 +77,9 @@ def test_qkv_split_transposed_v(cuda):
 @pytest.mark.parametrize('NB,H,W,cs,N,act', [(2, 14, 19, [64], 64, 'none'), (1, 37, 50, [128], 256, 'relu'),
                                              (2, 28, 37, [32, 64, 64], 32, 'relu'), (1, 56, 74, [192], 192, 'none'),
                                              (1, 30, 41, [8], 32, 'relu'), (3, 16, 16, [544], 544, 'relu')])
-def test_conv3x3(cuda, NB, H, W, cs, N, act):
+@pytest.mark.parametrize('tile', [None, (8, 16)])
+def test_conv3x3(cuda, NB, H, W, cs, N, act, tile):
+    """tile=None: halo-tile kernel (one A fetch per chunk); tile=(8,16): generic per-tap TMA kernel."""
     ops = _ops()
     g = torch.Generator(device='cuda').manual_seed(H * W + N)
     ctot = sum(cs)
@@ -87,7 +89,7 @@ def test_conv3x3(cuda, NB, H, W, cs, N, act):
     pw = ops.pack_weight(w, b, src_c=cs)
     srcs = [to_nhwc(x) for x in xs]
     out = torch.zeros(NB, H, W, ops.pad_to(N, 8), dtype=torch.bfloat16, device=cuda)
-    ops.gemm(pw, srcs, out, image=(NB, H, W), act=ops.ACT_RELU if act == 'relu' else ops.ACT_NONE)
+    ops.gemm(pw, srcs, out, image=(NB, H, W), act=ops.ACT_RELU if act == 'relu' else ops.ACT_NONE, tile=tile)
     ref = F.conv2d(torch.cat([rb(x) for x in xs], 1), rb(w), b, padding=1)
     if act == 'relu':
         ref = F.relu(ref)
@@ -142,3 +144,33 @@ def test_conv_transpose(cuda, k, Cin, Cout, H, W):
     ops.gemm_convT(pw, src, (NB, H, W), out)
     ref = F.conv_transpose2d(rb(x), rb(w), b, stride=k)
     check('convT k%d %d->%d' % (k, Cin, Cout), from_nhwc(out, Cout), ref, 1e-2)
+
+
+def test_fused_trailing_layer(cuda):
+    """conv/linear + activation with a narrow second 1x1 layer folded into the epilogue (heads 80->4, 128->nA, 32->1)."""
+    ops = _ops()
+    g = torch.Generator(device='cuda').manual_seed(11)
+    NB, H, W = 2, 30, 41
+    for cs, N, n2, act, act2, skip in [([32, 128], 80, 4, 'gelu', 'softplus', True), ([128], 32, 1, 'relu', 'relu', False),
+                                       ([128], 128, 16, 'relu', 'softplus', True)]:
+        xs = [torch.randn(NB, c, H, W, device=cuda, generator=g) for c in cs]
+        taps = 9 if N == 32 else 1
+        k = 3 if taps == 9 else 1
+        w = torch.randn(N, sum(cs), k, k, device=cuda, generator=g) / (taps * sum(cs)) ** 0.5
+        b = torch.randn(N, device=cuda, generator=g)
+        w2 = torch.randn(n2, N, device=cuda, generator=g) / N ** 0.5
+        b2 = torch.randn(n2, device=cuda, generator=g)
+        pw = ops.pack_weight(w, b, src_c=cs)
+        out = torch.full((NB, H, W, ops.pad_to(N, 8)), 5.0, dtype=torch.bfloat16, device=cuda)
+        out3 = torch.zeros(NB, H, W, 32, dtype=torch.float32, device=cuda)
+        A = dict(relu=ops.ACT_RELU, gelu=ops.ACT_GELU, softplus=ops.ACT_SOFTPLUS)
+        ops.gemm(pw, [to_nhwc(x) for x in xs], out, image=(NB, H, W), act=A[act], tail=(w2, b2, A[act2]),
+                 tail_out=out3, skip_main=skip)
+        fa = dict(relu=F.relu, gelu=F.gelu, softplus=F.softplus)
+        mid = fa[act](F.conv2d(torch.cat([rb(x) for x in xs], 1), rb(w), b, padding=k // 2))
+        ref = fa[act2](F.conv2d(mid, w2.view(n2, N, 1, 1), b2))
+        check('fused tail %s->%d->%d' % (cs, N, n2), out3[..., :n2].permute(0, 3, 1, 2), ref, 2e-3)
+        if skip:
+            assert (out == 5.0).all(), 'main output must not be written'
+        else:
+            check('main output', from_nhwc(out, N), mid, 1e-2)
