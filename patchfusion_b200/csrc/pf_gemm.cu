@@ -35,6 +35,7 @@ struct GemmKernelParams {
   int stages;
   int total_tiles;
   int k_steps;  // per tile
+  int kc;       // halo kernel: taps per weight stage (1, 3 or 9)
 };
 
 struct TileCoord {
@@ -391,9 +392,11 @@ __global__ void __launch_bounds__(kGemmThreads, 1) pf_conv3_halo_kernel(const __
   const GemmDesc& d = P.d;
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int stages = P.stages;                              // B ring
+  const int kc = P.kc;                                      // taps per B stage
   const int b_tile_bytes = d.block_n * kBlockK * 2;
+  const int b_stage_bytes = kc * b_tile_bytes;
   uint8_t* smem_b = smem + kHaloSlots * kHaloSlot;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_b + stages * b_tile_bytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_b + stages * b_stage_bytes);
   uint64_t* a_full = bars;                                  // [kHaloSlots]
   uint64_t* a_empty = a_full + kHaloSlots;
   uint64_t* b_full = a_empty + kHaloSlots;                  // [stages]
@@ -432,10 +435,12 @@ __global__ void __launch_bounds__(kGemmThreads, 1) pf_conv3_halo_kernel(const __
             mbar_expect_tx(&a_full[as], kHaloBytes);
             tma_load_4d(smem + as * kHaloSlot, &P.tmA[s], &a_full[as], ch * kBlockK, c.x0 - 1, c.y0 - 1, c.img);
             if (++as == kHaloSlots) { as = 0; aph ^= 1; }
-            for (int tap = 0; tap < 9; ++tap) {
+            for (int tap0 = 0; tap0 < 9; tap0 += kc) {
               mbar_wait(&b_empty[bs], bph ^ 1);
-              mbar_expect_tx(&b_full[bs], b_tile_bytes);
-              tma_load_2d(smem_b + bs * b_tile_bytes, &P.tmB, &b_full[bs], (kbase + tap * nch + ch) * kBlockK, c.n0);
+              mbar_expect_tx(&b_full[bs], b_stage_bytes);
+              for (int j = 0; j < kc; ++j)
+                tma_load_2d(smem_b + bs * b_stage_bytes + j * b_tile_bytes, &P.tmB, &b_full[bs],
+                            (kbase + (tap0 + j) * nch + ch) * kBlockK, c.n0);
               if (++bs == stages) { bs = 0; bph ^= 1; }
             }
           }
@@ -460,18 +465,24 @@ __global__ void __launch_bounds__(kGemmThreads, 1) pf_conv3_halo_kernel(const __
             tc_fence_after();
             const uint32_t halo = smem_u32(smem + as * kHaloSlot);
 #pragma unroll 1
-            for (int tap = 0; tap < 9; ++tap) {
-              const int dy = tap / 3, dx = tap - dy * 3;
+            for (int tap0 = 0; tap0 < 9; tap0 += kc) {
               mbar_wait(&b_full[bs], bph);
               tc_fence_after();
-              // A view: rows (dy*10 + dx) + 10*g + i, g = image row of the tile, i = pixel within the 8-wide row
-              uint64_t adesc = umma_desc_k128(halo + (dy * kHaloW + dx) * 128);
-              adesc = (adesc & ~(static_cast<uint64_t>(0x3FFF) << 32)) | (static_cast<uint64_t>((kHaloW * 128) >> 4) << 32);
-              const uint64_t bdesc = umma_desc_k128(smem_u32(smem_b + bs * b_tile_bytes));
+              const uint32_t bstage = smem_u32(smem_b + bs * b_stage_bytes);
+#pragma unroll 1
+              for (int j = 0; j < kc; ++j) {
+                const int tap = tap0 + j;
+                const int dy = tap / 3, dx = tap - dy * 3;
+                // A view: rows (dy*10 + dx) + 10*g + i, g = image row of the tile, i = pixel within the 8-wide row
+                uint64_t adesc = umma_desc_k128(halo + (dy * kHaloW + dx) * 128);
+                adesc = (adesc & ~(static_cast<uint64_t>(0x3FFF) << 32)) |
+                        (static_cast<uint64_t>((kHaloW * 128) >> 4) << 32);
+                const uint64_t bdesc = umma_desc_k128(bstage + j * b_tile_bytes);
 #pragma unroll
-              for (int k = 0; k < kBlockK / 16; ++k) {
-                umma_bf16(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, first ? 0u : 1u);
-                first = 0;
+                for (int k = 0; k < kBlockK / 16; ++k) {
+                  umma_bf16(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, first ? 0u : 1u);
+                  first = 0;
+                }
               }
               umma_commit(&b_empty[bs]);
               if (++bs == stages) { bs = 0; bph ^= 1; }
@@ -517,6 +528,7 @@ int gemm_launch(const GemmDesc& d, const CUtensorMap* tmA, const CUtensorMap& tm
   for (int s = d.num_src; s < 3; ++s) P.tmA[s] = tmA[0];
   P.tmB = tmB;
   P.d = d;
+  P.kc = 1;
   int stage_bytes = kATileBytes + d.block_n * kBlockK * 2;
   int budget = kMaxSmem - 1024 /*align*/ - 256 /*barriers*/;
   int stages = budget / stage_bytes;
@@ -539,8 +551,14 @@ int gemm_launch(const GemmDesc& d, const CUtensorMap* tmA, const CUtensorMap& tm
     }
     int b_bytes = d.block_n * kBlockK * 2;
     int hb = kMaxSmem - 1024 - 512 - kHaloSlots * kHaloSlot;
+    // taps per weight stage: amortise the per-stage barrier round trip (~500 clk) over >= ~512 clk of MMA work
+    int kc = 1;
+    if (9 * b_bytes * 2 <= hb) kc = 9;
+    else if (3 * b_bytes * 2 <= hb && d.block_n < 256) kc = 3;
+    P.kc = kc;
+    b_bytes *= kc;
     int hstages = hb / b_bytes;
-    if (hstages > 8) hstages = 8;
+    if (hstages > 6) hstages = 6;
     if (hstages < 2) return set_error("conv3 halo: not enough shared memory");
     P.stages = hstages;
     size_t hsmem = 1024 + static_cast<size_t>(kHaloSlots) * kHaloSlot + static_cast<size_t>(hstages) * b_bytes + 512;
