@@ -156,7 +156,7 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
 // that follows) - ~3x fewer instructions than erff in the GEMM epilogue.
 __device__ __forceinline__ float gelu_erf(float x) {
   const float u = fabsf(x) * 0.70710678118654752440f;
-  const float t = __frcp_rn(fmaf(0.3275911f, u, 1.0f));
+  const float t = __fdividef(1.0f, fmaf(0.3275911f, u, 1.0f));     // MUFU.RCP, 1 ulp: invisible after the bf16 store
   float p = fmaf(t, 1.061405429f, -1.453152027f);
   p = fmaf(t, p, 1.421413741f);
   p = fmaf(t, p, -0.284496736f);

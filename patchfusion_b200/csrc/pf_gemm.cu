@@ -26,7 +26,8 @@ namespace pf {
 constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;
 constexpr int kATileBytes = kBlockM * kBlockK * 2;  // 16 KiB
-constexpr int kGemmThreads = 192;
+constexpr int kEpiWarps = 8;                       // two warps per TMEM lane quadrant split the column chunks
+constexpr int kGemmThreads = 64 + kEpiWarps * 32;  // + TMA producer warp + MMA/TMEM warp
 
 struct GemmKernelParams {
   CUtensorMap tmA[3];
@@ -66,6 +67,7 @@ __device__ __forceinline__ TileCoord decode_tile(const GemmDesc& d, int t) {
 // (vector loads/stores, no predication); the tail variant predicates every column but keeps all indices static so
 // f[] stays in registers.
 constexpr int kMaxTail = 16;   // widest fused trailing 1x1 layer
+constexpr int kTailBytes = 512 + 128 * kMaxTail * 4;   // barriers + TMEM slot + [128][kMaxTail] fp32 scratch
 
 template <bool FULL>
 __device__ __forceinline__ void epilogue_chunk(const GemmDesc& d, float (&f)[32], long long orow, int ncol, int lcol,
@@ -200,8 +202,10 @@ __device__ __forceinline__ void epilogue_chunk(const GemmDesc& d, float (&f)[32]
 
 // Epilogue warps (4 warps, TMEM lane quadrant = warp & 3): drain accumulator stage `acc` of each tile this CTA owns.
 __device__ __forceinline__ void epilogue_loop(const GemmDesc& d, int total_tiles, uint64_t* tmem_full,
-                                              uint64_t* tmem_empty, uint32_t tmem_base, int warp, int lane) {
+                                              uint64_t* tmem_empty, uint32_t tmem_base, int warp, int lane,
+                                              float* tail_smem) {
   const int q = warp & 3;                 // TMEM lane quadrant this warp may access
+  const int half = (warp - 2) >> 2;       // which of the quadrant's two warps: takes every other 32-column chunk
   const int r = q * 32 + lane;            // accumulator row owned by this thread
   int acc = 0; uint32_t acc_phase = 0;
   for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
@@ -237,7 +241,7 @@ __device__ __forceinline__ void epilogue_loop(const GemmDesc& d, int total_tiles
     float y2[kMaxTail];
 #pragma unroll
     for (int i = 0; i < kMaxTail; ++i) y2[i] = 0.f;
-    for (int cb = 0; cb < d.block_n; cb += 32) {
+    for (int cb = half * 32; cb < d.block_n; cb += 64) {
       uint32_t v[32];
       tmem_ld32(taddr + cb, v);
       tmem_ld_wait();
@@ -255,7 +259,21 @@ __device__ __forceinline__ void epilogue_loop(const GemmDesc& d, int total_tiles
         epilogue_chunk<false>(d, f, orow, ncol, lcol, nvalid, y2);
       }
     }
-    if (d.w2 != nullptr && row_ok) {
+    if (d.w2 != nullptr) {
+      // combine the two half-row partial sums of the fused trailing layer through shared memory
+      float* ts = tail_smem + r * kMaxTail;
+      if (half == 1) {
+#pragma unroll
+        for (int i = 0; i < kMaxTail; ++i) ts[i] = y2[i];
+      }
+      asm volatile("bar.sync %0, 64;" ::"r"(q + 1) : "memory");
+      if (half == 0) {
+#pragma unroll
+        for (int i = 0; i < kMaxTail; ++i) y2[i] += ts[i];
+      }
+      asm volatile("bar.sync %0, 64;" ::"r"(q + 1) : "memory");
+    }
+    if (d.w2 != nullptr && row_ok && half == 0) {
       // trailing layer output: fp32 [rows, out3_ld], bias + activation
       float* op = d.out3 + orow * d.out3_ld;
 #pragma unroll
@@ -288,6 +306,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) pf_gemm_kernel(const __grid_c
   uint64_t* tmem_full = empty_bar + stages;   // [2]
   uint64_t* tmem_empty = tmem_full + 2;       // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  float* tail_smem = reinterpret_cast<float*>(tmem_slot + 4);   // [128][kMaxTail]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -296,7 +315,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) pf_gemm_kernel(const __grid_c
     for (int s = 0; s < d.num_src; ++s) prefetch_tmap(&P.tmA[s]);
     prefetch_tmap(&P.tmB);
     for (int s = 0; s < stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], 128); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], kEpiWarps * 32); }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, 512);
@@ -360,7 +379,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) pf_gemm_kernel(const __grid_c
     }
   } else {
     // ===================== epilogue (warps 2..5) =====================
-    epilogue_loop(d, P.total_tiles, tmem_full, tmem_empty, tmem_base, warp, lane);
+    epilogue_loop(d, P.total_tiles, tmem_full, tmem_empty, tmem_base, warp, lane, tail_smem);
   }
 
   tc_fence_before();
@@ -404,6 +423,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) pf_conv3_halo_kernel(const __
   uint64_t* tmem_full = b_empty + stages;                   // [2]
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  float* tail_smem = reinterpret_cast<float*>(tmem_slot + 4);   // [128][kMaxTail]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -412,7 +432,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) pf_conv3_halo_kernel(const __
     prefetch_tmap(&P.tmB);
     for (int s = 0; s < kHaloSlots; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
     for (int s = 0; s < stages; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], 128); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], kEpiWarps * 32); }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, 512);
@@ -496,7 +516,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) pf_conv3_halo_kernel(const __
       }
     }
   } else {
-    epilogue_loop(d, P.total_tiles, tmem_full, tmem_empty, tmem_base, warp, lane);
+    epilogue_loop(d, P.total_tiles, tmem_full, tmem_empty, tmem_base, warp, lane, tail_smem);
   }
   tc_fence_before();
   __syncthreads();
@@ -530,7 +550,7 @@ int gemm_launch(const GemmDesc& d, const CUtensorMap* tmA, const CUtensorMap& tm
   P.d = d;
   P.kc = 1;
   int stage_bytes = kATileBytes + d.block_n * kBlockK * 2;
-  int budget = kMaxSmem - 1024 /*align*/ - 256 /*barriers*/;
+  int budget = kMaxSmem - 1024 /*align*/ - kTailBytes /*barriers + fused-tail scratch*/;
   int stages = budget / stage_bytes;
   if (stages > 8) stages = 8;
   if (stages < 2) return set_error("gemm: not enough shared memory for 2 stages");
@@ -541,7 +561,7 @@ int gemm_launch(const GemmDesc& d, const CUtensorMap* tmA, const CUtensorMap& tm
   P.total_tiles = d.m_tiles * d.n_tiles;
   if (P.total_tiles <= 0 || ks <= 0) return set_error("gemm: empty problem");
   int grid = P.total_tiles < g_sm_count ? P.total_tiles : g_sm_count;
-  size_t smem = 1024 + static_cast<size_t>(stages) * stage_bytes + 256;
+  size_t smem = 1024 + static_cast<size_t>(stages) * stage_bytes + kTailBytes;
   if (d.halo) {
     static bool halo_attr = false;
     if (!halo_attr) {
@@ -550,7 +570,7 @@ int gemm_launch(const GemmDesc& d, const CUtensorMap* tmA, const CUtensorMap& tm
       halo_attr = true;
     }
     int b_bytes = d.block_n * kBlockK * 2;
-    int hb = kMaxSmem - 1024 - 512 - kHaloSlots * kHaloSlot;
+    int hb = kMaxSmem - 1024 - kTailBytes - kHaloSlots * kHaloSlot;
     // taps per weight stage: amortise the per-stage barrier round trip (~500 clk) over >= ~512 clk of MMA work
     int kc = 1;
     if (9 * b_bytes * 2 <= hb) kc = 9;
@@ -561,7 +581,7 @@ int gemm_launch(const GemmDesc& d, const CUtensorMap* tmA, const CUtensorMap& tm
     if (hstages > 6) hstages = 6;
     if (hstages < 2) return set_error("conv3 halo: not enough shared memory");
     P.stages = hstages;
-    size_t hsmem = 1024 + static_cast<size_t>(kHaloSlots) * kHaloSlot + static_cast<size_t>(hstages) * b_bytes + 512;
+    size_t hsmem = 1024 + static_cast<size_t>(kHaloSlots) * kHaloSlot + static_cast<size_t>(hstages) * b_bytes + kTailBytes;
     pf_conv3_halo_kernel<<<grid, kGemmThreads, hsmem, stream>>>(P);
   } else {
     pf_gemm_kernel<<<grid, kGemmThreads, smem, stream>>>(P);
