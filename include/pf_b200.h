@@ -167,6 +167,9 @@ int pf_stitch_accumulate(float* num, float* den, int32_t CH, int32_t CW, const f
                          int32_t tw, const int32_t* origins, const float* mask, int32_t up_h, int32_t up_w,
                          void* stream);
 int pf_stitch_finalize(const float* num, const float* den, int64_t n, float* out, void* stream);
+/* Multi-GPU tile sharding: `stack` is the all-gathered [world][2][n] (num, den) canvases; sums over ranks in rank
+ * order into stack[0] (deterministic for a fixed world size). */
+int pf_stitch_reduce(float* stack, int32_t world, int64_t n, void* stream);
 /* RunningAverageMap.resize (utils.py:32-36): num' = nearest(avg) * bilinear_ac(cnt), den' = bilinear_ac(cnt) */
 int pf_stitch_resize(const float* num, const float* den, int32_t H, int32_t W, int32_t OH, int32_t OW, float* num_out,
                      float* den_out, void* stream);

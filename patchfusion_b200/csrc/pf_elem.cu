@@ -542,6 +542,15 @@ __global__ void stitch_finalize_kernel(const float* __restrict__ num, const floa
   if (i < n) out[i] = num[i] / den[i];
 }
 
+// num[0] <- sum_r num[r], den[0] <- sum_r den[r] over the all-gathered per-rank canvases (fixed rank order).
+__global__ void stitch_reduce_kernel(float* __restrict__ stack, int world, long long n) {
+  long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (i >= 2 * n) return;
+  float s = 0.f;
+  for (int r = 0; r < world; ++r) s += stack[static_cast<long long>(r) * 2 * n + i];
+  stack[i] = s;
+}
+
 __global__ void stitch_resize_kernel(const float* __restrict__ num, const float* __restrict__ den, int H, int W, int OH,
                                      int OW, float* __restrict__ num_out, float* __restrict__ den_out) {
   long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
@@ -732,6 +741,11 @@ int pf_stitch_accumulate(float* num, float* den, int32_t CH, int32_t CW, const f
 int pf_stitch_finalize(const float* num, const float* den, int64_t n, float* out, void* stream) {
   stitch_finalize_kernel<<<nblocks(n, 256), 256, 0, ST>>>(num, den, n, out);
   return check_launch("stitch_finalize_kernel");
+}
+
+int pf_stitch_reduce(float* stack, int32_t world, int64_t n, void* stream) {
+  stitch_reduce_kernel<<<nblocks(2 * n, 256), 256, 0, ST>>>(stack, world, n);
+  return check_launch("stitch_reduce_kernel");
 }
 
 int pf_stitch_resize(const float* num, const float* den, int32_t H, int32_t W, int32_t OH, int32_t OW, float* num_out,

@@ -67,6 +67,7 @@ SIGNATURES = {
     'pf_logbinom_depth': [_p, _i, _p, _i, _i, _i, _i, _i, _i, _f, _f, _p, _p],
     'pf_stitch_accumulate': [_p, _p, _i, _i, _p, _i, _i, _i, _p, _p, _i, _i, _p],
     'pf_stitch_finalize': [_p, _p, _ll, _p, _p],
+    'pf_stitch_reduce': [_p, _i, _ll, _p],
     'pf_stitch_resize': [_p, _p, _i, _i, _i, _i, _p, _p, _p],
 }
 EXPORTS = sorted(list(SIGNATURES) + ['pf_last_error', 'pf_version', 'pf_launch_count'])

@@ -250,6 +250,17 @@ class PatchFusion(ParamTree, PyTorchModelHubMixin):
         ops.call('pf_stitch_accumulate', num, den, CH, CW, pred, T, ph, pw, io['dst'], mask, up[0], up[1],
                  ops.stream_ptr())
 
+    def _combine_canvases(self, num, den, base=None):
+        """ONE all-gather of the stacked (num, den) canvases + fixed-order sum (pf_stitch_reduce)."""
+        from . import ops
+        from .parallel import gather_canvases
+        stack = gather_canvases(num, den)
+        ops.call('pf_stitch_reduce', stack, stack.shape[0], ops.C.c_int64(num.numel()), ops.stream_ptr())
+        n, d = stack[0, 0], stack[0, 1]
+        if base is not None:
+            n, d = n + base[0], d + base[1]
+        return n.contiguous(), d.contiguous()
+
     def _tile_io(self, eng, T):
         return dict(raw=eng.buf('tile.raw', (T, 2), torch.int32), dst=eng.buf('tile.dst', (T, 2), torch.int32),
                     boxes=eng.buf('tile.boxes', (T, 4), torch.float32))
@@ -278,7 +289,9 @@ class PatchFusion(ParamTree, PyTorchModelHubMixin):
 
     @torch.no_grad()
     def forward(self, mode, image_lr, image_hr, depth_gt=None, crops_image_hr=None, crop_depths=None, bboxs=None,
-                tile_cfg=None, cai_mode='m1', process_num=4):
+                tile_cfg=None, cai_mode='m1', process_num=4, shard=None):
+        """`shard=(rank, world)` (extension): process only this rank's tiles and combine the canvases with one
+        all-gather (patchfusion_b200/parallel.py); None reproduces the reference's single-device behaviour."""
         if mode == 'train':
             raise NotImplementedError('training is out of scope of the B200 hot-path build (SURVEY.md §2 rows 10,12)')
         from . import ops
@@ -320,18 +333,36 @@ class PatchFusion(ParamTree, PyTorchModelHubMixin):
             ny, nx = (H - oy) // h, (W - ox) // w
             raw += [(h * a + oy, w * b + ox) for a in range(ny) for b in range(nx)]
             proc += [(ph * a + py, pw * b + px) for a in range(ny) for b in range(nx)]
-        self._run_tiles(eng, img, raw, proc, geom, (num, den, RH, RW), mask, (0, 0), process_num)
+        if shard is not None:
+            from .parallel import shard_indices
+            own = shard_indices(len(raw), shard[0], shard[1])
+            raw, proc = [raw[i] for i in own], [proc[i] for i in own]
+        if raw:
+            self._run_tiles(eng, img, raw, proc, geom, (num, den, RH, RW), mask, (0, 0), process_num)
+        if shard is not None:
+            num, den = self._combine_canvases(num, den)
         if cai_mode[0] == 'r':
             mask = self._mask((h, w), dev)
             n2 = eng.buf('canvas.num_raw', (H, W), torch.float32)
             d2 = eng.buf('canvas.den_raw', (H, W), torch.float32)
             ops.call('pf_stitch_resize', num, den, RH, RW, H, W, n2, d2, st())
             num, den = n2, d2
+            if shard is not None:
+                # the resized regular-phase canvas is identical on every rank: keep it aside so the all-gather of the
+                # random phase only sums the per-rank increments
+                n2_base, d2_base = n2.clone(), d2.clone()
+                n2.zero_()
+                d2.zero_()
             for _ in range(int(cai_mode[1:]) // process_num):
                 ys = [random.randint(0, H - h - 1) for _ in range(process_num)]     # baseline_pretrain.py:155-156
                 x0 = random.randint(0, W - w - 1)
                 raw = [(y, x0) for y in ys]
-                self._run_tiles(eng, img, raw, raw, geom, (num, den, H, W), mask, (h, w), process_num)
+                if shard is not None:        # every rank draws the same boxes (same `random` state), owns a slice
+                    raw = [raw[i] for i in shard_indices(len(raw), shard[0], shard[1])]
+                if raw:
+                    self._run_tiles(eng, img, raw, raw, geom, (num, den, H, W), mask, (h, w), process_num)
+            if shard is not None:
+                num, den = self._combine_canvases(num, den, base=(n2_base, d2_base))
         out = torch.empty_like(num)
         ops.call('pf_stitch_finalize', num, den, ops.C.c_int64(num.numel()), out, st())
         depth = out[None, None]
