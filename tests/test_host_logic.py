@@ -78,3 +78,11 @@ def test_hf_round_trip(tmp_path):
     a, b = m.state_dict(), m2.state_dict()
     assert list(a) == list(b) and all(torch.equal(a[k], b[k]) for k in a)
     assert m2.config.coarse_branch.midas_model_type == 'vits'
+
+
+def test_reference_import_path_and_registry():
+    from estimator.models import build_model
+    from estimator.models.patchfusion import PatchFusion as PF
+    assert PF is PatchFusion
+    m = build_model(dict(type='PatchFusion', config=depth_anything_patchfusion('vits')))
+    assert isinstance(m, PatchFusion) and m.patch_process_shape == [392, 518]
