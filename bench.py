@@ -142,6 +142,16 @@ def cpu_baseline(encoder, cfg, sd, threads=None, reps=1, warm=0):
                 s_per_tile=t_tile, s_fixed_per_image=t_fixed, tile_times=ts)
 
 
+def lib_summary(records):
+    out = {}
+    for fam, fl, e0, e1 in records:
+        d = out.setdefault(fam, dict(ms=0.0, flops=0.0, launches=0))
+        d['ms'] += e0.elapsed_time(e1)
+        d['flops'] += fl
+        d['launches'] += 1
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
@@ -150,7 +160,7 @@ def main():
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--encoder', default='vitl')
     ap.add_argument('--cai-mode', default='m2')
-    ap.add_argument('--process-num', type=int, default=7)
+    ap.add_argument('--process-num', type=int, default=9)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--profile', action='store_true', help='per-kernel-family time table to stderr')
     args = ap.parse_args()
@@ -243,11 +253,12 @@ def main():
     clocks = sampler.stop() if sampler else {}
 
     # roofline pass: per-launch CUDA events around every kernel of one more step (not part of the timed value)
-    prof = None
+    prof_records = None
     if rank == 0:
         lib.PROFILER = lib.Profiler()
         step(img_dev)
-        prof = lib.PROFILER.summary()
+        torch.cuda.synchronize()
+        prof_records = lib.PROFILER.records
         lib.PROFILER = None
     barrier()
 
@@ -257,13 +268,31 @@ def main():
     if rank != 0:
         return
     pk = peaks()
-    gm = prof.get('pf_gemm', dict(ms=1.0, flops=0.0, launches=0))
-    total_ms = sum(v['ms'] for v in prof.values())
-    ach = gm['flops'] / (gm['ms'] / 1e3) / 1e12
-    roof = dict(bound='tensor', achieved=ach, peak=pk['tflops_sustained'], unit='TFLOP/s', frac=ach / pk['tflops_sustained'],
-                traffic=None, kernel='pf_gemm_kernel (tcgen05 implicit GEMM; %d launches/step, %.1f%% of step kernel time)' %
-                (gm['launches'], 100.0 * gm['ms'] / total_ms), peak_source=pk['source'] + ', sustained bf16',
+    fam = lib_summary(prof_records)
+    total_ms = sum(v['ms'] for v in fam.values())
+    halo = fam.get('pf_conv3_halo', dict(ms=1e-9, flops=0.0, launches=0))
+    gall_ms = halo['ms'] + fam.get('pf_gemm', dict(ms=0.0))['ms']
+    gall_fl = halo['flops'] + fam.get('pf_gemm', dict(flops=0.0))['flops']
+    # dominant kernel = pf_conv3_halo_kernel; its heaviest launch shape = guided_fusion.up_conv_list.4 conv1
+    # (3x3, [32,256,256] -> 544 channels @392x518), timed per launch with CUDA events on the launching stream
+    big = max((r for r in prof_records if r[0] == 'pf_conv3_halo'), key=lambda r: r[1])
+    same = [r for r in prof_records if r[0] == 'pf_conv3_halo' and r[1] == big[1]]
+    ms_launch = sum(r[2].elapsed_time(r[3]) for r in same) / len(same)
+    ach = big[1] / (ms_launch / 1e3) / 1e12
+    rows_launch = big[1] / (2.0 * 9 * 544 * 544)
+    # DRAM bytes of this launch shape from the committed ncu --set full capture (profiles/r01_halo_conv_up4_full.md:
+    # 1.600 GB read + 1.505 GB written for 7 tiles = 1,421,392 output pixels), scaled to this launch's pixel count
+    traffic = (1.600068e9 + 1.505072e9) / 1421392.0 * rows_launch
+    roof = dict(bound='tensor', achieved=ach, peak=pk['tflops_sustained'], unit='TFLOP/s',
+                frac=ach / pk['tflops_sustained'], traffic=traffic,
+                kernel='pf_conv3_halo_kernel (tcgen05 halo-tile 3x3 conv; %d launches/step, %.1f%% of step kernel '
+                       'time); launch = up_conv_list.4 conv1 [32,256,256]->544 @392x518 x %d tiles, %.3f ms'
+                       % (halo['launches'], 100.0 * halo['ms'] / total_ms, round(rows_launch / (392 * 518)), ms_launch),
+                algorithmic_bytes=rows_launch * (544 + 544) * 2.0 + 544 * 9 * 576 * 2.0,
+                peak_source=pk['source'] + ', sustained bf16',
+                all_gemm_tflops=gall_fl / (gall_ms / 1e3) / 1e12, all_gemm_share=gall_ms / total_ms,
                 whole_step_tflops=(tps / world * F_TILE[enc] + tps / world / n_tiles * F_IMAGE[enc]) / 1e12)
+    prof = fam
     if args.profile:
         for k_, v in sorted(prof.items(), key=lambda kv: -kv[1]['ms']):
             sys.stderr.write('%-26s %8.2f ms %6d launches %8.1f TF/s\n' % (k_, v['ms'], v['launches'],

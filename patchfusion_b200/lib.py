@@ -117,6 +117,7 @@ class Profiler:
     def __init__(self):
         self.records = []
         self.next_flops = 0.0
+        self.next_family = None
 
     def summary(self):
         torch.cuda.synchronize()
@@ -136,10 +137,11 @@ def call(name, *args):
     if PROFILER is not None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         fl, PROFILER.next_flops = PROFILER.next_flops, 0.0
+        fam, PROFILER.next_family = PROFILER.next_family or name, None
         e0.record()
         _call(name, *args)
         e1.record()
-        PROFILER.records.append((name, fl, e0, e1))
+        PROFILER.records.append((fam, fl, e0, e1))
     else:
         _call(name, *args)
 

@@ -140,6 +140,8 @@ def gemm(pw, srcs, out, *, image=None, ps_image=None, M=None, act=ACT_NONE, res1
     if lib.PROFILER is not None:
         n_true = pw.ps_cout * pw.ps * pw.ps if pw.ps > 1 else pw.N
         lib.PROFILER.next_flops = 2.0 * rows * sum(cs) * pw.taps * n_true
+        if d.a_mode == 1 and pw.taps == 9 and tile is None:
+            lib.PROFILER.next_family = 'pf_conv3_halo'
     call('pf_gemm', C.byref(d), stream_ptr())
     return d
 
