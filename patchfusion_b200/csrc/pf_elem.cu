@@ -127,8 +127,18 @@ __global__ void f32_to_bf16_kernel(const float* __restrict__ in, long long n, bf
 
 // ------------------------------------------------------------------------------------------------ resampling
 // align_corners=True source coordinate exactly as ATen: scale = (in-1)/(out-1) (0 when out == 1), src = scale*dst.
+__host__ __device__ __forceinline__ float ac_scale(int in, int out) {
+  return out > 1 ? static_cast<float>(in - 1) / static_cast<float>(out - 1) : 0.f;
+}
+__device__ __forceinline__ void ac_coord_s(int dst, int in, float scale, int& lo, int& hi, float& frac) {
+  float src = scale * dst;
+  lo = static_cast<int>(src);
+  if (lo > in - 1) lo = in - 1;
+  hi = lo + (lo < in - 1 ? 1 : 0);
+  frac = src - lo;
+}
 __device__ __forceinline__ void ac_coord(int dst, int in, int out, int& lo, int& hi, float& frac) {
-  float scale = out > 1 ? static_cast<float>(in - 1) / static_cast<float>(out - 1) : 0.f;
+  float scale = ac_scale(in, out);
   float src = scale * dst;
   lo = static_cast<int>(src);
   if (lo > in - 1) lo = in - 1;
@@ -136,30 +146,30 @@ __device__ __forceinline__ void ac_coord(int dst, int in, int out, int& lo, int&
   frac = src - lo;
 }
 
-__global__ void resize_bilinear_kernel(const bf16* __restrict__ in, int B, int H, int W, int C, int in_ld, int OH,
-                                       int OW, bf16* __restrict__ out, int out_ld, int out_col0) {
-  const int cg = C >> 3;
-  long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
-  long long total = static_cast<long long>(B) * OH * OW * cg;
-  if (idx >= total) return;
-  int g = static_cast<int>(idx % cg);
-  long long p = idx / cg;
-  int ox = static_cast<int>(p % OW);
-  long long t = p / OW;
-  int oy = static_cast<int>(t % OH);
-  int b = static_cast<int>(t / OH);
+// grid: (ceil(OW*cg / 256), OH, B); thread = (output pixel x, 8-channel group).  32-bit index math only, row
+// coordinates and scales hoisted (the 64-bit div/mod version spent most of its time on address arithmetic).
+__global__ void resize_bilinear_kernel(const bf16* __restrict__ in, int H, int W, int cg, int in_ld, int OH, int OW,
+                                       float sy, float sx, bf16* __restrict__ out, int out_ld, int out_col0) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= OW * cg) return;
+  const int ox = t / cg, g = t - ox * cg;
+  const int oy = blockIdx.y, b = blockIdx.z;
   int y0, y1, x0, x1; float fy, fx;
-  ac_coord(oy, H, OH, y0, y1, fy);
-  ac_coord(ox, W, OW, x0, x1, fx);
-  const bf16* base = in + static_cast<long long>(b) * H * W * in_ld + g * 8;
+  ac_coord_s(oy, H, sy, y0, y1, fy);
+  ac_coord_s(ox, W, sx, x0, x1, fx);
+  const bf16* base = in + static_cast<size_t>(b) * H * W * in_ld + g * 8;
+  const bf16* r0 = base + static_cast<size_t>(y0) * W * in_ld;
+  const bf16* r1 = base + static_cast<size_t>(y1) * W * in_ld;
+  const uint4 u00 = __ldg(reinterpret_cast<const uint4*>(r0 + static_cast<size_t>(x0) * in_ld));
+  const uint4 u01 = __ldg(reinterpret_cast<const uint4*>(r0 + static_cast<size_t>(x1) * in_ld));
+  const uint4 u10 = __ldg(reinterpret_cast<const uint4*>(r1 + static_cast<size_t>(x0) * in_ld));
+  const uint4 u11 = __ldg(reinterpret_cast<const uint4*>(r1 + static_cast<size_t>(x1) * in_ld));
   float a[8], bb[8], c[8], d[8], o[8];
-  unpack8(*reinterpret_cast<const uint4*>(base + (static_cast<long long>(y0) * W + x0) * in_ld), a);
-  unpack8(*reinterpret_cast<const uint4*>(base + (static_cast<long long>(y0) * W + x1) * in_ld), bb);
-  unpack8(*reinterpret_cast<const uint4*>(base + (static_cast<long long>(y1) * W + x0) * in_ld), c);
-  unpack8(*reinterpret_cast<const uint4*>(base + (static_cast<long long>(y1) * W + x1) * in_ld), d);
+  unpack8(u00, a); unpack8(u01, bb); unpack8(u10, c); unpack8(u11, d);
   const float w00 = (1.f - fy) * (1.f - fx), w01 = (1.f - fy) * fx, w10 = fy * (1.f - fx), w11 = fy * fx;
 #pragma unroll
   for (int i = 0; i < 8; ++i) o[i] = w00 * a[i] + w01 * bb[i] + w10 * c[i] + w11 * d[i];
+  const size_t p = (static_cast<size_t>(b) * OH + oy) * OW + ox;
   *reinterpret_cast<uint4*>(out + p * out_ld + out_col0 + g * 8) = pack8(o);
 }
 
@@ -193,33 +203,29 @@ __device__ __forceinline__ bool roi_coord(float c, int size, int& lo, int& hi, f
   return true;
 }
 
+// grid: (ceil(w*cg / 256), h, T); thread = (output pixel x, 8-channel group [bf16] or channel [fp32]).
 template <bool F32>
-__global__ void roi_crop_zoom_kernel(const void* __restrict__ feat, int h, int w, int C, int in_ld,
-                                     const float* __restrict__ boxes, int T, float scale, void* __restrict__ out,
+__global__ void roi_crop_zoom_kernel(const void* __restrict__ feat, int h, int w, int cg, int in_ld,
+                                     const float* __restrict__ boxes, float scale, void* __restrict__ out,
                                      int out_ld, int out_col0) {
-  const int cg = F32 ? C : (C >> 3);
-  long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
-  long long total = static_cast<long long>(T) * h * w * cg;
-  if (idx >= total) return;
-  int g = static_cast<int>(idx % cg);
-  long long p = idx / cg;
-  int ox = static_cast<int>(p % w);
-  long long t2 = p / w;
-  int oy = static_cast<int>(t2 % h);
-  int t = static_cast<int>(t2 / h);
-  const float x1 = boxes[t * 4 + 0] * scale - 0.5f, y1 = boxes[t * 4 + 1] * scale - 0.5f;
-  const float x2 = boxes[t * 4 + 2] * scale - 0.5f, y2 = boxes[t * 4 + 3] * scale - 0.5f;
+  const int tt = blockIdx.x * blockDim.x + threadIdx.x;
+  if (tt >= w * cg) return;
+  const int ox = tt / cg, g = tt - ox * cg;
+  const int oy = blockIdx.y, t = blockIdx.z;
+  const float x1 = __ldg(boxes + t * 4 + 0) * scale - 0.5f, y1 = __ldg(boxes + t * 4 + 1) * scale - 0.5f;
+  const float x2 = __ldg(boxes + t * 4 + 2) * scale - 0.5f, y2 = __ldg(boxes + t * 4 + 3) * scale - 0.5f;
   const float bw = (x2 - x1) / w, bh = (y2 - y1) / h;
   const float sy = y1 + (oy + 0.5f) * bh, sx = x1 + (ox + 0.5f) * bw;
   int yl, yh, xl, xh; float fy, fx;
   bool ok = roi_coord(sy, h, yl, yh, fy);
   ok = roi_coord(sx, w, xl, xh, fx) && ok;
+  const size_t p = (static_cast<size_t>(t) * h + oy) * w + ox;
   if (F32) {
     const float* f = static_cast<const float*>(feat) + g;
     float v = 0.f;
     if (ok) {
-      float v00 = f[(static_cast<long long>(yl) * w + xl) * in_ld], v01 = f[(static_cast<long long>(yl) * w + xh) * in_ld];
-      float v10 = f[(static_cast<long long>(yh) * w + xl) * in_ld], v11 = f[(static_cast<long long>(yh) * w + xh) * in_ld];
+      float v00 = f[(static_cast<size_t>(yl) * w + xl) * in_ld], v01 = f[(static_cast<size_t>(yl) * w + xh) * in_ld];
+      float v10 = f[(static_cast<size_t>(yh) * w + xl) * in_ld], v11 = f[(static_cast<size_t>(yh) * w + xh) * in_ld];
       v = (1.f - fy) * (1.f - fx) * v00 + (1.f - fy) * fx * v01 + fy * (1.f - fx) * v10 + fy * fx * v11;
     }
     static_cast<float*>(out)[p * out_ld + out_col0 + g] = v;
@@ -230,10 +236,10 @@ __global__ void roi_crop_zoom_kernel(const void* __restrict__ feat, int h, int w
     if (ok) {
       const bf16* f = static_cast<const bf16*>(feat) + g * 8;
       float a[8], bb[8], c[8], d[8];
-      unpack8(*reinterpret_cast<const uint4*>(f + (static_cast<long long>(yl) * w + xl) * in_ld), a);
-      unpack8(*reinterpret_cast<const uint4*>(f + (static_cast<long long>(yl) * w + xh) * in_ld), bb);
-      unpack8(*reinterpret_cast<const uint4*>(f + (static_cast<long long>(yh) * w + xl) * in_ld), c);
-      unpack8(*reinterpret_cast<const uint4*>(f + (static_cast<long long>(yh) * w + xh) * in_ld), d);
+      unpack8(__ldg(reinterpret_cast<const uint4*>(f + (static_cast<size_t>(yl) * w + xl) * in_ld)), a);
+      unpack8(__ldg(reinterpret_cast<const uint4*>(f + (static_cast<size_t>(yl) * w + xh) * in_ld)), bb);
+      unpack8(__ldg(reinterpret_cast<const uint4*>(f + (static_cast<size_t>(yh) * w + xl) * in_ld)), c);
+      unpack8(__ldg(reinterpret_cast<const uint4*>(f + (static_cast<size_t>(yh) * w + xh) * in_ld)), d);
       const float w00 = (1.f - fy) * (1.f - fx), w01 = (1.f - fy) * fx, w10 = fy * (1.f - fx), w11 = fy * fx;
 #pragma unroll
       for (int i = 0; i < 8; ++i) o[i] = w00 * a[i] + w01 * bb[i] + w10 * c[i] + w11 * d[i];
@@ -434,79 +440,102 @@ __global__ void add_upsampled_kernel(const bf16* __restrict__ a, int B, int H, i
   *reinterpret_cast<uint4*>(out + p * C + g * 8) = pack8(o);
 }
 
-// one thread per (pixel, bin): b = up(b_prev); b += mean_a( dx / (1 + 300 dx^2) ), dx = A_a - b.
+// one warp per pixel (grid-stride), 2 bins per lane (nbins == 64): b = up(b_prev); b += mean_a( dx / (1 + 300 dx^2) ),
+// dx = A_a - b.  The <= 16 attractor points of the pixel are read once per warp.
 __global__ void attractor_kernel(const float* __restrict__ A, int A_ld, int nA, const float* __restrict__ b_prev, int PH,
-                                 int PW, int B, int H, int W, int nbins, int kind_mean, float* __restrict__ b_out) {
-  long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
-  long long total = static_cast<long long>(B) * H * W * nbins;
-  if (idx >= total) return;
-  int k = static_cast<int>(idx % nbins);
-  long long p = idx / nbins;
-  int ox = static_cast<int>(p % W);
-  long long t = p / W;
-  int oy = static_cast<int>(t % H);
-  int b = static_cast<int>(t / H);
-  int y0, y1, x0, x1; float fy, fx;
-  ac_coord(oy, PH, H, y0, y1, fy);
-  ac_coord(ox, PW, W, x0, x1, fx);
-  const float* base = b_prev + static_cast<long long>(b) * PH * PW * nbins + k;
-  float v00 = base[(static_cast<long long>(y0) * PW + x0) * nbins], v01 = base[(static_cast<long long>(y0) * PW + x1) * nbins];
-  float v10 = base[(static_cast<long long>(y1) * PW + x0) * nbins], v11 = base[(static_cast<long long>(y1) * PW + x1) * nbins];
-  float bc = (1.f - fy) * ((1.f - fx) * v00 + fx * v01) + fy * ((1.f - fx) * v10 + fx * v11);
-  const float* Ap = A + p * A_ld;
-  float s = 0.f;
-  for (int a = 0; a < nA; ++a) {
-    float dx = Ap[a] - bc;
-    s += dx / (1.f + 300.f * dx * dx);
+                                 int PW, int B, int H, int W, int nbins, int kind_mean, float sy, float sx,
+                                 float* __restrict__ b_out) {
+  const int lane = threadIdx.x & 31;
+  const int warps = (gridDim.x * blockDim.x) >> 5;
+  const int total = B * H * W, hw = H * W;
+  for (int p = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; p < total; p += warps) {
+    const int b = p / hw, rem = p - b * hw;
+    const int oy = rem / W, ox = rem - oy * W;
+    int y0, y1, x0, x1; float fy, fx;
+    ac_coord_s(oy, PH, sy, y0, y1, fy);
+    ac_coord_s(ox, PW, sx, x0, x1, fx);
+    const float* base = b_prev + static_cast<size_t>(b) * PH * PW * nbins;
+    const float* r00 = base + (static_cast<size_t>(y0) * PW + x0) * nbins;
+    const float* r01 = base + (static_cast<size_t>(y0) * PW + x1) * nbins;
+    const float* r10 = base + (static_cast<size_t>(y1) * PW + x0) * nbins;
+    const float* r11 = base + (static_cast<size_t>(y1) * PW + x1) * nbins;
+    const float av = lane < nA ? __ldg(A + static_cast<size_t>(p) * A_ld + lane) : 0.f;
+    float bc[2], s[2] = {0.f, 0.f};
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int k = lane + 32 * i;
+      bc[i] = (1.f - fy) * ((1.f - fx) * __ldg(r00 + k) + fx * __ldg(r01 + k)) +
+              fy * ((1.f - fx) * __ldg(r10 + k) + fx * __ldg(r11 + k));
+    }
+    for (int a = 0; a < nA; ++a) {
+      const float aa = __shfl_sync(0xffffffffu, av, a);
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const float dx = aa - bc[i];
+        s[i] += dx / (1.f + 300.f * dx * dx);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      if (kind_mean) s[i] /= nA;
+      b_out[static_cast<size_t>(p) * nbins + lane + 32 * i] = bc[i] + s[i];
+    }
   }
-  if (kind_mean) s /= nA;
-  b_out[idx] = bc + s;
 }
 
-// one warp per pixel, 2 bins per lane (nbins == 64).
+// one warp per pixel (grid-stride), 2 bins per lane (nbins == 64); the Stirling log C(K-1,k) terms depend on the
+// lane only and are computed once per thread.
 __global__ void logbinom_depth_kernel(const float* __restrict__ pt, int pt_ld, const float* __restrict__ bc, int BH, int BW,
-                                      int B, int H, int W, int nbins, float min_t, float max_t, float* __restrict__ depth) {
-  long long p = blockIdx.x * static_cast<long long>(blockDim.x >> 5) + (threadIdx.x >> 5);
-  int lane = threadIdx.x & 31;
-  long long total = static_cast<long long>(B) * H * W;
-  if (p >= total) return;
-  int ox = static_cast<int>(p % W);
-  long long t = p / W;
-  int oy = static_cast<int>(t % H);
-  int b = static_cast<int>(t / H);
-  const float* q = pt + p * pt_ld;
-  float p0 = q[0] + 1e-4f, p1 = q[1] + 1e-4f, t0 = q[2] + 1e-4f, t1 = q[3] + 1e-4f;
-  float pr = p0 / (p0 + p1);
-  float tt = t0 / (t0 + t1);
-  tt = (max_t - min_t) * tt + min_t;
-  float om = fminf(fmaxf(1.f - pr, 1e-4f), 1.f);
-  pr = fminf(fmaxf(pr, 1e-4f), 1.f);
-  const float lp = logf(pr), lq = logf(om);
-  int y0, y1, x0, x1; float fy, fx;
-  ac_coord(oy, BH, H, y0, y1, fy);
-  ac_coord(ox, BW, W, x0, x1, fx);
-  const float* base = bc + static_cast<long long>(b) * BH * BW * nbins;
+                                      int B, int H, int W, int nbins, float min_t, float max_t, float sy, float sx,
+                                      float* __restrict__ depth) {
+  const int lane = threadIdx.x & 31;
+  const int warps = (gridDim.x * blockDim.x) >> 5;
+  const int total = B * H * W;
   const float Km1 = static_cast<float>(nbins - 1);
-  float yv[2], cv[2];
-  float mx = -INFINITY;
+  float logc[2], kf[2];
 #pragma unroll
   for (int i = 0; i < 2; ++i) {
-    int k = lane + 32 * i;
-    float kf = static_cast<float>(k);
-    float n_ = Km1 + 1e-7f, k_ = kf + 1e-7f;
-    float logc = n_ * logf(n_) - k_ * logf(k_) - (n_ - k_) * logf(n_ - k_ + 1e-7f);
-    yv[i] = (logc + kf * lp + (Km1 - kf) * lq) / tt;
-    mx = fmaxf(mx, yv[i]);
-    float v00 = base[(static_cast<long long>(y0) * BW + x0) * nbins + k], v01 = base[(static_cast<long long>(y0) * BW + x1) * nbins + k];
-    float v10 = base[(static_cast<long long>(y1) * BW + x0) * nbins + k], v11 = base[(static_cast<long long>(y1) * BW + x1) * nbins + k];
-    cv[i] = (1.f - fy) * ((1.f - fx) * v00 + fx * v01) + fy * ((1.f - fx) * v10 + fx * v11);
+    kf[i] = static_cast<float>(lane + 32 * i);
+    float n_ = Km1 + 1e-7f, k_ = kf[i] + 1e-7f;
+    logc[i] = n_ * logf(n_) - k_ * logf(k_) - (n_ - k_) * logf(n_ - k_ + 1e-7f);
   }
+  const int hw = H * W;
+  for (int p = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; p < total; p += warps) {
+    const int b = p / hw, rem = p - b * hw;
+    const int oy = rem / W, ox = rem - oy * W;
+    const float4 q = __ldg(reinterpret_cast<const float4*>(pt + static_cast<size_t>(p) * pt_ld));
+    float p0 = q.x + 1e-4f, p1 = q.y + 1e-4f, t0 = q.z + 1e-4f, t1 = q.w + 1e-4f;
+    float pr = p0 / (p0 + p1);
+    float tt = t0 / (t0 + t1);
+    tt = (max_t - min_t) * tt + min_t;
+    float om = fminf(fmaxf(1.f - pr, 1e-4f), 1.f);
+    pr = fminf(fmaxf(pr, 1e-4f), 1.f);
+    const float lp = logf(pr), lq = logf(om), inv_t = 1.f / tt;
+    int y0, y1, x0, x1; float fy, fx;
+    ac_coord_s(oy, BH, sy, y0, y1, fy);
+    ac_coord_s(ox, BW, sx, x0, x1, fx);
+    const float* base = bc + static_cast<size_t>(b) * BH * BW * nbins;
+    const float* r00 = base + (static_cast<size_t>(y0) * BW + x0) * nbins;
+    const float* r01 = base + (static_cast<size_t>(y0) * BW + x1) * nbins;
+    const float* r10 = base + (static_cast<size_t>(y1) * BW + x0) * nbins;
+    const float* r11 = base + (static_cast<size_t>(y1) * BW + x1) * nbins;
+    float yv[2], cv[2];
+    float mx = -INFINITY;
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-  float e0 = expf(yv[0] - mx), e1 = expf(yv[1] - mx);
-  float den = warp_sum(e0 + e1);
-  float num = warp_sum(e0 * cv[0] + e1 * cv[1]);
-  if (lane == 0) depth[p] = num / den;
+    for (int i = 0; i < 2; ++i) {
+      const int k = lane + 32 * i;
+      yv[i] = (logc[i] + kf[i] * lp + (Km1 - kf[i]) * lq) * inv_t;
+      mx = fmaxf(mx, yv[i]);
+      cv[i] = (1.f - fy) * ((1.f - fx) * __ldg(r00 + k) + fx * __ldg(r01 + k)) +
+              fy * ((1.f - fx) * __ldg(r10 + k) + fx * __ldg(r11 + k));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    float e0 = __expf(yv[0] - mx), e1 = __expf(yv[1] - mx);
+    float den = warp_sum(e0 + e1);
+    float num = warp_sum(e0 * cv[0] + e1 * cv[1]);
+    if (lane == 0) depth[p] = num / den;
+  }
 }
 
 // ------------------------------------------------------------------------------------------------ stitch
@@ -605,9 +634,10 @@ int pf_f32_to_bf16(const float* in, int64_t n, void* out, void* stream) {
 int pf_resize_bilinear(const void* in, int32_t B, int32_t H, int32_t W, int32_t C, int32_t in_ld, int32_t OH,
                        int32_t OW, void* out, int32_t out_ld, int32_t out_col0, void* stream) {
   if (C % 8 || in_ld % 8 || out_ld % 8 || out_col0 % 8) return set_error("pf_resize_bilinear: channel counts/strides must be multiples of 8");
-  long long total = static_cast<long long>(B) * OH * OW * (C / 8);
-  resize_bilinear_kernel<<<nblocks(total, 256), 256, 0, ST>>>(static_cast<const bf16*>(in), B, H, W, C, in_ld, OH, OW,
-                                                               static_cast<bf16*>(out), out_ld, out_col0);
+  const int cg = C / 8;
+  dim3 grid(nblocks(static_cast<long long>(OW) * cg, 256), OH, B);
+  resize_bilinear_kernel<<<grid, 256, 0, ST>>>(static_cast<const bf16*>(in), H, W, cg, in_ld, OH, OW, ac_scale(H, OH),
+                                               ac_scale(W, OW), static_cast<bf16*>(out), out_ld, out_col0);
   return check_launch("resize_bilinear_kernel");
 }
 
@@ -622,14 +652,13 @@ int pf_roi_crop_zoom(const void* feat, int32_t in_f32, int32_t h, int32_t w, int
                      const float* boxes, int32_t T, float spatial_scale, void* out, int32_t out_ld, int32_t out_col0,
                      void* stream) {
   if (in_f32) {
-    long long total = static_cast<long long>(T) * h * w * C;
-    roi_crop_zoom_kernel<true><<<nblocks(total, 256), 256, 0, ST>>>(feat, h, w, C, in_ld, boxes, T, spatial_scale, out,
-                                                                    out_ld, out_col0);
+    dim3 grid(nblocks(static_cast<long long>(w) * C, 256), h, T);
+    roi_crop_zoom_kernel<true><<<grid, 256, 0, ST>>>(feat, h, w, C, in_ld, boxes, spatial_scale, out, out_ld, out_col0);
   } else {
     if (C % 8 || in_ld % 8 || out_ld % 8 || out_col0 % 8) return set_error("pf_roi_crop_zoom: channels/strides must be multiples of 8");
-    long long total = static_cast<long long>(T) * h * w * (C / 8);
-    roi_crop_zoom_kernel<false><<<nblocks(total, 256), 256, 0, ST>>>(feat, h, w, C, in_ld, boxes, T, spatial_scale, out,
-                                                                     out_ld, out_col0);
+    dim3 grid(nblocks(static_cast<long long>(w) * (C / 8), 256), h, T);
+    roi_crop_zoom_kernel<false><<<grid, 256, 0, ST>>>(feat, h, w, C / 8, in_ld, boxes, spatial_scale, out, out_ld,
+                                                      out_col0);
   }
   return check_launch("roi_crop_zoom_kernel");
 }
@@ -715,17 +744,20 @@ int pf_add_upsampled(const void* a, int32_t B, int32_t H, int32_t W, int32_t C, 
 
 int pf_attractor(const float* A, int32_t A_ld, int32_t nA, const float* b_prev, int32_t PH, int32_t PW, int32_t B,
                  int32_t H, int32_t W, int32_t nbins, int32_t kind_mean, float* b_out, void* stream) {
-  long long total = static_cast<long long>(B) * H * W * nbins;
-  attractor_kernel<<<nblocks(total, 256), 256, 0, ST>>>(A, A_ld, nA, b_prev, PH, PW, B, H, W, nbins, kind_mean, b_out);
+  if (nbins != 64 || nA > 32) return set_error("pf_attractor: n_bins must be 64 and n_attractors <= 32");
+  long long warps_needed = static_cast<long long>(B) * H * W;
+  unsigned blocks = static_cast<unsigned>(warps_needed < 148 * 8 * 8 ? (warps_needed + 7) / 8 : 148 * 8);
+  attractor_kernel<<<blocks, 256, 0, ST>>>(A, A_ld, nA, b_prev, PH, PW, B, H, W, nbins, kind_mean, ac_scale(PH, H),
+                                           ac_scale(PW, W), b_out);
   return check_launch("attractor_kernel");
 }
 
 int pf_logbinom_depth(const float* pt, int32_t pt_ld, const float* b_centers, int32_t BH, int32_t BW, int32_t B,
                       int32_t H, int32_t W, int32_t nbins, float min_temp, float max_temp, float* depth, void* stream) {
   if (nbins != 64) return set_error("pf_logbinom_depth: n_bins must be 64");
-  long long total = static_cast<long long>(B) * H * W;
-  logbinom_depth_kernel<<<nblocks(total, 8), 256, 0, ST>>>(pt, pt_ld, b_centers, BH, BW, B, H, W, nbins, min_temp,
-                                                            max_temp, depth);
+  if (pt_ld % 4) return set_error("pf_logbinom_depth: pt_ld must be a multiple of 4");
+  logbinom_depth_kernel<<<148 * 8, 256, 0, ST>>>(pt, pt_ld, b_centers, BH, BW, B, H, W, nbins, min_temp, max_temp,
+                                                 ac_scale(BH, H), ac_scale(BW, W), depth);
   return check_launch("logbinom_depth_kernel");
 }
 
