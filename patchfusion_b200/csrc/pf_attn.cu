@@ -17,6 +17,12 @@ namespace pf {
 constexpr int kAttnThreads = 192;
 constexpr int kQTile = 128, kKTile = 128, kHd = 64;
 
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 struct AttnParams {
   CUtensorMap tmQK;   // 3-D {2*D, seq, B}, box {64, 128, 1}
   CUtensorMap tmVt;   // 2-D {seq_pad, B*heads*64}, box {64, 64}
@@ -131,35 +137,46 @@ __global__ void __launch_bounds__(kAttnThreads, 2) pf_attention_kernel(const __g
       const int kvalid = min(kKTile, P.seq - j * kKTile);   // keys of this block that exist
       mbar_wait(s_full, ph);
       tc_fence_after();
-      // pass 1: row max (scores in log2 units)
-      float m_blk = -INFINITY;
+      // pass 1: row max of the raw scores (scale > 0, applied once afterwards)
+      float m_raw = -INFINITY;
+      const bool full = kvalid == kKTile;
 #pragma unroll 1
       for (int cb = 0; cb < kKTile; cb += 32) {
         uint32_t v[32];
         tmem_ld32(tmem_S + lane_sel + cb, v);
         tmem_ld_wait();
+        if (full) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i)
-          if (cb + i < kvalid) m_blk = fmaxf(m_blk, __uint_as_float(v[i]) * P.scale_log2);
+          for (int i = 0; i < 32; ++i) m_raw = fmaxf(m_raw, __uint_as_float(v[i]));
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (cb + i < kvalid) m_raw = fmaxf(m_raw, __uint_as_float(v[i]));
+        }
       }
-      const float m_new = fmaxf(m_run, m_blk);
-      const float alpha = exp2f(m_run - m_new);
+      const float m_new = fmaxf(m_run, m_raw * P.scale_log2);
+      const float alpha = ex2_approx(m_run - m_new);
       float l_blk = 0.0f;
-      // pass 2: p = 2^(s - m), bf16 -> swizzled smem tile
+      // pass 2: p = 2^(s*scale - m) (one FFMA + one MUFU per score), bf16 pairs -> swizzled smem tile
 #pragma unroll 1
       for (int cb = 0; cb < kKTile; cb += 32) {
         uint32_t v[32];
         tmem_ld32(tmem_S + lane_sel + cb, v);
         tmem_ld_wait();
         float p[32];
+        if (full) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          float e = exp2f(__uint_as_float(v[i]) * P.scale_log2 - m_new);
-          e = (cb + i < kvalid) ? e : 0.0f;
-          // accumulate the denominator from the bf16-rounded value actually fed to the PV product
-          float eb = __bfloat162float(__float2bfloat16(e));
-          l_blk += eb;
-          p[i] = eb;
+          for (int i = 0; i < 32; ++i) {
+            p[i] = ex2_approx(fmaf(__uint_as_float(v[i]), P.scale_log2, -m_new));
+            l_blk += p[i];
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            float e = ex2_approx(fmaf(__uint_as_float(v[i]), P.scale_log2, -m_new));
+            p[i] = (cb + i < kvalid) ? e : 0.0f;
+            l_blk += p[i];
+          }
         }
         uint8_t* sub = sP + (cb >> 6) * 16384 + r * 128;
 #pragma unroll
