@@ -205,9 +205,13 @@ def main():
     host_out = torch.empty((1, 1, RH, RW), dtype=torch.float32).pin_memory()
     gathered = torch.empty((world, RH, RW), dtype=torch.float32, device=dev) if world > 1 else None
 
-    def step(img_dev):
+    def local_step(img_dev):
         lr = model.make_lr(img_dev)
         y, _ = model(mode='infer', image_lr=lr, image_hr=img_dev, cai_mode=args.cai_mode, process_num=args.process_num)
+        return y
+
+    def step(img_dev):
+        y = local_step(img_dev)
         if world > 1:
             import torch.distributed as dist
             dist.all_gather_into_tensor(gathered, y[0, 0].contiguous())
@@ -256,7 +260,7 @@ def main():
     prof_records = None
     if rank == 0:
         lib.PROFILER = lib.Profiler()
-        step(img_dev)
+        local_step(img_dev)                 # no collective here: only rank 0 runs this pass
         torch.cuda.synchronize()
         prof_records = lib.PROFILER.records
         lib.PROFILER = None
