@@ -137,43 +137,52 @@ __global__ void __launch_bounds__(kAttnThreads, 2) pf_attention_kernel(const __g
       const int kvalid = min(kKTile, P.seq - j * kKTile);   // keys of this block that exist
       mbar_wait(s_full, ph);
       tc_fence_after();
-      // pass 1: row max of the raw scores (scale > 0, applied once afterwards)
+      // pass 1: row max of the raw scores (scale > 0, applied once afterwards).  TMEM loads are software
+      // pipelined: chunk i+1 is in flight while chunk i is consumed.
       float m_raw = -INFINITY;
       const bool full = kvalid == kKTile;
-#pragma unroll 1
-      for (int cb = 0; cb < kKTile; cb += 32) {
-        uint32_t v[32];
-        tmem_ld32(tmem_S + lane_sel + cb, v);
-        tmem_ld_wait();
+      uint32_t va[32], vb[32];
+      tmem_ld32(tmem_S + lane_sel, va);
+      tmem_ld_wait();
+#pragma unroll
+      for (int c2 = 0; c2 < kKTile / 32; ++c2) {
+        uint32_t (&cur)[32] = (c2 & 1) ? vb : va;
+        uint32_t (&nxt)[32] = (c2 & 1) ? va : vb;
+        // after the last score chunk, prefetch chunk 0 again for pass 2
+        tmem_ld32(tmem_S + lane_sel + ((c2 + 1) & 3) * 32, nxt);
+        const int cb = c2 * 32;
         if (full) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) m_raw = fmaxf(m_raw, __uint_as_float(v[i]));
+          for (int i = 0; i < 32; ++i) m_raw = fmaxf(m_raw, __uint_as_float(cur[i]));
         } else {
 #pragma unroll
           for (int i = 0; i < 32; ++i)
-            if (cb + i < kvalid) m_raw = fmaxf(m_raw, __uint_as_float(v[i]));
+            if (cb + i < kvalid) m_raw = fmaxf(m_raw, __uint_as_float(cur[i]));
         }
+        tmem_ld_wait();
       }
       const float m_new = fmaxf(m_run, m_raw * P.scale_log2);
       const float alpha = ex2_approx(m_run - m_new);
       float l_blk = 0.0f;
-      // pass 2: p = 2^(s*scale - m) (one FFMA + one MUFU per score), bf16 pairs -> swizzled smem tile
-#pragma unroll 1
-      for (int cb = 0; cb < kKTile; cb += 32) {
-        uint32_t v[32];
-        tmem_ld32(tmem_S + lane_sel + cb, v);
-        tmem_ld_wait();
+      // pass 2: p = 2^(s*scale - m) (one FFMA + one MUFU per score), bf16 pairs -> swizzled smem tile.
+      // (va holds chunk 0 again at this point)
+#pragma unroll
+      for (int c2 = 0; c2 < kKTile / 32; ++c2) {
+        uint32_t (&cur)[32] = (c2 & 1) ? vb : va;
+        uint32_t (&nxt)[32] = (c2 & 1) ? va : vb;
+        if (c2 + 1 < kKTile / 32) tmem_ld32(tmem_S + lane_sel + (c2 + 1) * 32, nxt);
+        const int cb = c2 * 32;
         float p[32];
         if (full) {
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
-            p[i] = ex2_approx(fmaf(__uint_as_float(v[i]), P.scale_log2, -m_new));
+            p[i] = ex2_approx(fmaf(__uint_as_float(cur[i]), P.scale_log2, -m_new));
             l_blk += p[i];
           }
         } else {
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
-            float e = ex2_approx(fmaf(__uint_as_float(v[i]), P.scale_log2, -m_new));
+            float e = ex2_approx(fmaf(__uint_as_float(cur[i]), P.scale_log2, -m_new));
             p[i] = (cb + i < kvalid) ? e : 0.0f;
             l_blk += p[i];
           }
@@ -186,6 +195,7 @@ __global__ void __launch_bounds__(kAttnThreads, 2) pf_attention_kernel(const __g
                                 pack_bf16(p[g * 8 + 4], p[g * 8 + 5]), pack_bf16(p[g * 8 + 6], p[g * 8 + 7]));
           *reinterpret_cast<uint4*>(sub + ((chunk ^ (r & 7)) << 4)) = pk;
         }
+        if (c2 + 1 < kKTile / 32) tmem_ld_wait();
       }
       l_run = l_run * alpha + l_blk;
       m_run = m_new;
@@ -195,13 +205,13 @@ __global__ void __launch_bounds__(kAttnThreads, 2) pf_attention_kernel(const __g
       // accumulate this block's P.V
       mbar_wait(o_full, ph);
       tc_fence_after();
+      tmem_ld32(tmem_O + lane_sel, va);
+      tmem_ld32(tmem_O + lane_sel + 32, vb);
+      tmem_ld_wait();
 #pragma unroll
-      for (int cb = 0; cb < kHd; cb += 32) {
-        uint32_t v[32];
-        tmem_ld32(tmem_O + lane_sel + cb, v);
-        tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 32; ++i) o_acc[cb + i] = o_acc[cb + i] * alpha + __uint_as_float(v[i]);
+      for (int i = 0; i < 32; ++i) {
+        o_acc[i] = fmaf(o_acc[i], alpha, __uint_as_float(va[i]));
+        o_acc[32 + i] = fmaf(o_acc[32 + i], alpha, __uint_as_float(vb[i]));
       }
       tc_fence_before();
       mbar_arrive(o_empty);

@@ -153,3 +153,84 @@ def test_infer_vs_reference_fixture(cuda, setup, mode):
     assert torch.isfinite(y).all()
     assert err / MAX_DEPTH < 1e-3
     assert err / (g.max() - g.min()).item() < 5e-2, 'error must also be small against the output range'
+
+
+def test_micro_batch_grouping_invariance(cuda, setup):
+    """Tiles are independent: m2 with process_num 2 / 4 / 9 (different micro-batch sizes, graphs and buffer sets)
+    gives the same canvas up to the fp32 order of the stitch's atomic adds."""
+    s = setup
+    model, img = s['model'], s['img']
+    lr = model.resizer(img)
+    outs = []
+    for pn in (2, 4, 9):
+        y, _ = model(mode='infer', image_lr=lr.to(cuda), image_hr=img.to(cuda), cai_mode='m2', process_num=pn)
+        outs.append(y.clone())
+    for y in outs[1:]:
+        err = (y - outs[0]).abs().max().item()
+        print('process_num invariance: max diff %.3e' % err)
+        assert err < 2e-3        # bf16 GEMM results are batch-size independent; only tile->CTA order may differ
+
+
+def test_vitl_full_size_tile_against_oracle(cuda):
+    """The flagship configuration (Depth-Anything-vitl, 4K, 4x4 split): coarse branch + two fused tiles through the
+    CUDA path against the oracle restatement executed by torch on the GPU in fp32 (TF32 off) - the CPU oracle needs
+    ~100 s per vitl tile.  Plus a size-independent property at full size: a canvas stitched from constant tiles is
+    that constant (partition of unity of the blend weights over all 49 tiles)."""
+    from oracle import pf_oracle as po
+    from patchfusion_b200 import ops
+    from patchfusion_b200.configs import depth_anything_patchfusion
+    from patchfusion_b200.model import PatchFusion
+    from patchfusion_b200.params import synthetic_state_dict
+    cfg = depth_anything_patchfusion('vitl')
+    sd = synthetic_state_dict(cfg, seed=0)
+    model = PatchFusion(cfg)
+    model.load_state_dict(sd, strict=True)
+    model = model.to(cuda).eval()
+    sdc = {k: v.to(cuda) for k, v in sd.items()}
+    del sd
+    img = torch.rand(1, 3, 2160, 3840, generator=torch.Generator().manual_seed(3)).to(cuda)
+    orc = po.Oracle(sdc, cfg)
+    lr = orc.resizer(img)
+    raw = [(540, 960), (810, 1440)]
+    H, W, h, w = 2160, 3840, 540, 960
+    P = cfg['patch_process_shape']
+    with torch.no_grad():
+        cd_o, cf_o = orc.coarse(lr)
+        g2l_o = po.g2l_all(sdc, cf_o, cfg['guided_fusion'])
+        tc = po.prepare_tile_cfg((H, W), (4, 4), P)
+        fu_o = orc.tiles(img, raw, cd_o, cf_o, g2l_o, 2, tc)
+    eng = model.engine()
+    cd, cf = eng.branch('coarse', lr.contiguous())
+    err_c = (cd[0] - cd_o[0, 0]).abs().max().item()
+    print('vitl coarse depth max-abs %.3e (range %.3f..%.3f)' % (err_c, cd_o.min().item(), cd_o.max().item()))
+    assert err_c / MAX_DEPTH < 1e-3 and err_c / (cd_o.max() - cd_o.min()).item() < 5e-2
+    for a, b in zip(cf, cf_o):
+        e = rel_err(a.t[..., :a.C].float().permute(0, 3, 1, 2), b)
+        assert e < 3e-2, e
+    model._coarse = (cd[0], cf, eng.g2l(cf))
+    for a, b in zip(model._coarse[2], g2l_o):
+        assert rel_err(a.t[..., :a.C].float().permute(0, 3, 1, 2), b) < 4e-2
+    num = torch.zeros(P[0] * 4, P[1] * 4, device=cuda)
+    den = torch.zeros_like(num)
+    io = model._tile_io(eng, 2)
+    io['raw'].copy_(torch.tensor(raw, dtype=torch.int32))
+    io['dst'].copy_(torch.tensor([(392, 518), (588, 777)], dtype=torch.int32))
+    fx, fy = np.float32(1 / W * P[1]), np.float32(1 / H * P[0])
+    io['boxes'].copy_(torch.tensor([[x * fx, y * fy, (x + w) * fx, (y + h) * fy] for (y, x) in raw], dtype=torch.float32))
+    mask = model._mask(P, cuda)
+    model._tiles_stage(eng, img[0].contiguous(), 2, (H, W, h, w, P[0], P[1]), (num, den, P[0] * 4, P[1] * 4), mask, (0, 0))
+    pred = eng.bufs[('fus.head.depth', (2, P[0], P[1]), torch.float32)]
+    err = (pred - fu_o[:, 0]).abs().max().item()
+    print('vitl fused tiles max-abs %.3e (range %.3f..%.3f)' % (err, fu_o.min().item(), fu_o.max().item()))
+    assert err / MAX_DEPTH < 1e-3 and err / (fu_o.max() - fu_o.min()).item() < 5e-2
+    # partition of unity at the full P49 geometry
+    tcf = po.prepare_tile_cfg((H, W), (4, 4), P)
+    plan = [t[1] for p in po.tile_plan(tcf, P, 'm2') for t in p]
+    assert len(plan) == 49
+    n2, d2 = torch.zeros_like(num), torch.zeros_like(den)
+    const = torch.full((49, P[0], P[1]), 3.25, device=cuda)
+    org = torch.tensor(plan, dtype=torch.int32, device=cuda)
+    ops.call('pf_stitch_accumulate', n2, d2, P[0] * 4, P[1] * 4, const, 49, P[0], P[1], org, mask, 0, 0, ops.stream_ptr())
+    out = torch.empty_like(n2)
+    ops.call('pf_stitch_finalize', n2, d2, ops.C.c_int64(n2.numel()), out, ops.stream_ptr())
+    assert (out - 3.25).abs().max().item() < 1e-5
