@@ -266,6 +266,10 @@ def main():
         lib.PROFILER = None
     barrier()
 
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+        dist.destroy_process_group()
     tiles_per_step = n_tiles * world
     tps = tiles_per_step * args.steps / (ms_dev / 1e3)
     tps_e2e = tiles_per_step * args.steps / (ms_e2e / 1e3)

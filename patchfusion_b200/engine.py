@@ -246,16 +246,17 @@ class Engine:
         return out
 
     # ------------------------------------------------------------------ one branch
-    def branch(self, which, images, taps=None):
+    def branch(self, which, images, taps=None, slot=''):
         """images: planar fp32 [B,3,H,W] in [0,1] (un-normalised).  Returns (depth fp32 [B,H,W], feats[6] Maps
-        low->high: x_d0, r4, r3, r2, r1, out_conv)."""
+        low->high: x_d0, r4, r3, r2, r1, out_conv).  `slot` selects an independent buffer set (double buffering of
+        the fine branch against the fusion stage of the previous micro-batch)."""
         Wd, hp = self.W[which], self.hp[which]
         B = images.shape[0]
         H, Wd_ = self.P
         gh, gw, D, C, oc = self.gh, self.gw, hp['dim'], hp['features'], hp['out_channels']
         npatch, seq = gh * gw, gh * gw + 1
         seq_pad = pad_to(seq, 8)
-        k = which + '.'
+        k = which + slot + '.'
         st = stream_ptr()
         # ---- tokens
         a0 = self.buf(k + 'im2col', (B * npatch, 592))
@@ -289,14 +290,14 @@ class Engine:
                     call('pf_layernorm', x[b * seq + 1:], D, Wd['nw'], Wd['nb'], ct.c_float(1e-6), npatch, D,
                          f[b], D, st)
                 feats.append(Map(f, D))
-        return self.dpt_and_head(which, feats, taps)
+        return self.dpt_and_head(which, feats, taps, slot)
 
-    def dpt_and_head(self, which, feats, taps=None):
+    def dpt_and_head(self, which, feats, taps=None, slot=''):
         Wd, hp = self.W[which], self.hp[which]
         B = feats[0].B
         gh, gw, C, oc = self.gh, self.gw, hp['features'], hp['out_channels']
         H, Wimg = self.P
-        k = which + '.dpt.'
+        k = which + slot + '.dpt.'
         st = stream_ptr()
         lay = []
         for i in range(4):
@@ -351,7 +352,7 @@ class Engine:
         blocks = [p4, p3, p2, p1]
         if taps is not None:
             taps['rel'] = rel.t[..., 0].clone()
-        depth = self.metric_head(which + '.head.', Wd['head'], hp, self.bcfg[which], x_d0, blocks, out_conv, rel, taps)
+        depth = self.metric_head(which + slot + '.head.', Wd['head'], hp, self.bcfg[which], x_d0, blocks, out_conv, rel, taps)
         return depth, [x_d0] + blocks + [out_conv]
 
     def metric_head(self, k, Wh, hp, bcfg, x, x_blocks, last, rel, taps=None):

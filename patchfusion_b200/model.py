@@ -114,6 +114,10 @@ class PatchFusion(ParamTree, PyTorchModelHubMixin):
         self.graph_launches = 0
         self._coarse = None
         self.use_cuda_graphs = os.environ.get('PF_B200_GRAPHS', '1') != '0'
+        self.partition = os.environ.get('PF_B200_PARTITION', 'greedy')
+        self.overlap = os.environ.get('PF_B200_OVERLAP', '1') != '0'
+        self._side_stream = None
+        self._fine_out = {}
         self._mask_cache = {}
         if config.load_branch:
             for which, path in zip(('coarse_branch', 'fine_branch'), config.pretrain_model):
@@ -235,20 +239,45 @@ class PatchFusion(ParamTree, PyTorchModelHubMixin):
         cd, cf = eng.branch('coarse', lr)
         self._coarse = (cd[0], cf, eng.g2l(cf))
 
-    def _tiles_stage(self, eng, img, T, geom, canvas, mask, up):
-        """crop+resize -> fine branch -> fusion -> scatter-stitch for one micro-batch of T tiles whose origins/boxes
-        sit in the static device buffers of `self._tile_io(T)`."""
+    def _fine_stage(self, eng, img, T, geom, par=0):
+        """crop+resize -> fine branch for the T tiles whose origins sit in the static buffers of `_tile_io(T, par)`."""
+        from . import ops
+        H, W, h, w, ph, pw = geom
+        io = self._tile_io(eng, T, par)
+        crops = eng.buf('tile.crops%d' % par, (T, 3, ph, pw), torch.float32)
+        ops.call('pf_crop_resize', img, H, W, io['raw'], T, h, w, ph, pw, crops, ops.stream_ptr())
+        fd, ff = eng.branch('fine', crops, slot=str(par) if par else '')
+        self._fine_out[par] = (crops, fd, ff)
+
+    def _fusion_stage(self, eng, T, geom, canvas, mask, up, par=0):
+        """guided fusion + scatter-stitch of the micro-batch whose fine-branch outputs sit in slot `par`."""
         from . import ops
         H, W, h, w, ph, pw = geom
         num, den, CH, CW = canvas
-        io = self._tile_io(eng, T)
+        io = self._tile_io(eng, T, par)
         cd, cf, g2l = self._coarse
-        crops = eng.buf('tile.crops', (T, 3, ph, pw), torch.float32)
-        ops.call('pf_crop_resize', img, H, W, io['raw'], T, h, w, ph, pw, crops, ops.stream_ptr())
-        fd, ff = eng.branch('fine', crops)
+        crops, fd, ff = self._fine_out[par]
         pred = eng.fusion(crops, io['boxes'], fd, ff, cd, cf, g2l)
         ops.call('pf_stitch_accumulate', num, den, CH, CW, pred, T, ph, pw, io['dst'], mask, up[0], up[1],
                  ops.stream_ptr())
+
+    def _tiles_stage(self, eng, img, T, geom, canvas, mask, up):
+        self._fine_stage(eng, img, T, geom, 0)
+        self._fusion_stage(eng, T, geom, canvas, mask, up, 0)
+
+    def _pair_stage(self, eng, img, geom, canvas, mask, up, fus, fine):
+        """fusion of micro-batch k (slot fus[1]) on the current stream while the fine branch of micro-batch k+1
+        (slot fine[1]) runs on a side stream: the two have no data dependency, so their kernels fill each other's
+        partial waves and launch gaps."""
+        cur = torch.cuda.current_stream()
+        if self._side_stream is None:
+            self._side_stream = torch.cuda.Stream()
+        side = self._side_stream
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            self._fine_stage(eng, img, fine[0], geom, fine[1])
+        self._fusion_stage(eng, fus[0], geom, canvas, mask, up, fus[1])
+        cur.wait_stream(side)
 
     def _combine_canvases(self, num, den, base=None):
         """ONE all-gather of the stacked (num, den) canvases + fixed-order sum (pf_stitch_reduce)."""
@@ -261,9 +290,10 @@ class PatchFusion(ParamTree, PyTorchModelHubMixin):
             n, d = n + base[0], d + base[1]
         return n.contiguous(), d.contiguous()
 
-    def _tile_io(self, eng, T):
-        return dict(raw=eng.buf('tile.raw', (T, 2), torch.int32), dst=eng.buf('tile.dst', (T, 2), torch.int32),
-                    boxes=eng.buf('tile.boxes', (T, 4), torch.float32))
+    def _tile_io(self, eng, T, par=0):
+        return dict(raw=eng.buf('tile.raw%d' % par, (T, 2), torch.int32),
+                    dst=eng.buf('tile.dst%d' % par, (T, 2), torch.int32),
+                    boxes=eng.buf('tile.boxes%d' % par, (T, 4), torch.float32))
 
     def _run_tiles(self, eng, img, raw, dst, geom, canvas, mask, up, process_num):
         H, W, h, w, ph, pw = geom
@@ -272,20 +302,40 @@ class PatchFusion(ParamTree, PyTorchModelHubMixin):
         # balanced micro-batches (e.g. 49 tiles, process_num 9 -> 9,8,8,8,8,8): at most two captured graph sizes
         # and no ragged tail; grouping does not change any tile's result
         nchunk = -(-len(raw) // process_num)
-        sizes = [len(raw) // nchunk + (1 if i < len(raw) % nchunk else 0) for i in range(nchunk)]
-        s = 0
-        for T in sizes:
-            chunk = raw[s:s + T]
-            io = self._tile_io(eng, T)
+        if self.partition == 'balanced':
+            sizes = [len(raw) // nchunk + (1 if i < len(raw) % nchunk else 0) for i in range(nchunk)]
+        else:                                   # 'greedy': full micro-batches + one remainder (the reference's split)
+            sizes = [min(process_num, len(raw) - i * process_num) for i in range(nchunk)]
+        def load_io(i, s0, par):
+            T = sizes[i]
+            chunk = raw[s0:s0 + T]
+            io = self._tile_io(eng, T, par)
             io['raw'].copy_(torch.tensor(chunk, dtype=torch.int32))
-            io['dst'].copy_(torch.tensor(dst[s:s + T], dtype=torch.int32))
+            io['dst'].copy_(torch.tensor(dst[s0:s0 + T], dtype=torch.int32))
             # boxes exactly as baseline_pretrain.py:268-282: int pixel box * fp32 factor
             bx = np.array([[np.float32(x) * fx, np.float32(y) * fy, np.float32(x + w) * fx, np.float32(y + h) * fy]
                            for (y, x) in chunk], dtype=np.float32)
             io['boxes'].copy_(torch.from_numpy(bx))
-            self._graphed(('tiles', T) + tuple(geom) + (canvas[2], canvas[3]) + tuple(up),
-                          lambda: self._tiles_stage(eng, img, T, geom, canvas, mask, up))
-            s += T
+
+        gkey = tuple(geom) + (canvas[2], canvas[3]) + tuple(up)
+        starts = [sum(sizes[:i]) for i in range(len(sizes))]
+        from . import lib
+        if not (self.overlap and self.use_cuda_graphs and lib.PROFILER is None and len(sizes) > 1):
+            for i, T in enumerate(sizes):
+                load_io(i, starts[i], 0)
+                self._graphed(('tiles', T) + gkey, lambda: self._tiles_stage(eng, img, T, geom, canvas, mask, up))
+            return
+        # software pipeline over micro-batches: fine(0) | fusion(k) || fine(k+1) | fusion(last)
+        load_io(0, starts[0], 0)
+        self._graphed(('fine', sizes[0], 0) + gkey, lambda: self._fine_stage(eng, img, sizes[0], geom, 0))
+        for i in range(len(sizes) - 1):
+            pf_, pn_ = i & 1, (i + 1) & 1
+            load_io(i + 1, starts[i + 1], pn_)
+            self._graphed(('pair', sizes[i], pf_, sizes[i + 1], pn_) + gkey,
+                          lambda: self._pair_stage(eng, img, geom, canvas, mask, up, (sizes[i], pf_), (sizes[i + 1], pn_)))
+        last = len(sizes) - 1
+        self._graphed(('fusion', sizes[last], last & 1) + gkey,
+                      lambda: self._fusion_stage(eng, sizes[last], geom, canvas, mask, up, last & 1))
 
     @torch.no_grad()
     def forward(self, mode, image_lr, image_hr, depth_gt=None, crops_image_hr=None, crop_depths=None, bboxs=None,
