@@ -115,7 +115,7 @@ class PatchFusion(ParamTree, PyTorchModelHubMixin):
         self._coarse = None
         self.use_cuda_graphs = os.environ.get('PF_B200_GRAPHS', '1') != '0'
         self.partition = os.environ.get('PF_B200_PARTITION', 'greedy')
-        self.overlap = os.environ.get('PF_B200_OVERLAP', '1') != '0'
+        self.overlap = os.environ.get('PF_B200_OVERLAP', '0') != '0'    # opt-in: +1 % on one GPU, see DESIGN.md
         self._side_stream = None
         self._fine_out = {}
         self._mask_cache = {}
