@@ -50,7 +50,8 @@ def test_resize_bilinear(cuda):
     from patchfusion_b200 import ops
     g = _gen(2)
     for (B, C, H, W, OH, OW) in [(2, 64, 14, 19, 28, 37), (1, 128, 224, 296, 392, 518), (2, 32, 49, 64, 56, 74),
-                                 (1, 8, 196, 259, 224, 296), (1, 64, 56, 74, 56, 74)]:
+                                 (1, 8, 196, 259, 224, 296), (1, 64, 56, 74, 56, 74), (2, 256, 112, 148, 224, 296),
+                                 (1, 64, 98, 129, 112, 148), (3, 192, 60, 70, 61, 207)]:
         x = torch.randn(B, C, H, W, device=cuda, generator=g)
         out = torch.zeros(B, OH, OW, C + 16, dtype=torch.bfloat16, device=cuda)
         ops.resize_bilinear(to_nhwc(x), C, OH, OW, out, out_col0=8)
