@@ -527,8 +527,8 @@ __global__ void attractor_kernel(const float* __restrict__ A, int A_ld, int nA, 
   }
 }
 
-// one warp per pixel (grid-stride), 2 bins per lane (nbins == 64); the Stirling log C(K-1,k) terms depend on the
-// lane only and are computed once per thread.
+// one warp per pixel (grid-stride), lane owns the adjacent bins (2*lane, 2*lane+1) so every bilinear tap is one
+// 8-byte load (nbins == 64); the Stirling log C(K-1,k) terms depend on the lane only and are computed once per thread.
 __global__ void logbinom_depth_kernel(const float* __restrict__ pt, int pt_ld, const float* __restrict__ bc, int BH, int BW,
                                       int B, int H, int W, int nbins, float min_t, float max_t, float sy, float sx,
                                       float* __restrict__ depth) {
@@ -539,7 +539,7 @@ __global__ void logbinom_depth_kernel(const float* __restrict__ pt, int pt_ld, c
   float logc[2], kf[2];
 #pragma unroll
   for (int i = 0; i < 2; ++i) {
-    kf[i] = static_cast<float>(lane + 32 * i);
+    kf[i] = static_cast<float>(2 * lane + i);
     float n_ = Km1 + 1e-7f, k_ = kf[i] + 1e-7f;
     logc[i] = n_ * logf(n_) - k_ * logf(k_) - (n_ - k_) * logf(n_ - k_ + 1e-7f);
   }
@@ -558,20 +558,19 @@ __global__ void logbinom_depth_kernel(const float* __restrict__ pt, int pt_ld, c
     int y0, y1, x0, x1; float fy, fx;
     ac_coord_s(oy, BH, sy, y0, y1, fy);
     ac_coord_s(ox, BW, sx, x0, x1, fx);
-    const float* base = bc + static_cast<size_t>(b) * BH * BW * nbins;
-    const float* r00 = base + (static_cast<size_t>(y0) * BW + x0) * nbins;
-    const float* r01 = base + (static_cast<size_t>(y0) * BW + x1) * nbins;
-    const float* r10 = base + (static_cast<size_t>(y1) * BW + x0) * nbins;
-    const float* r11 = base + (static_cast<size_t>(y1) * BW + x1) * nbins;
+    const float* base = bc + static_cast<size_t>(b) * BH * BW * nbins + 2 * lane;
+    const float2 c00 = __ldg(reinterpret_cast<const float2*>(base + (static_cast<size_t>(y0) * BW + x0) * nbins));
+    const float2 c01 = __ldg(reinterpret_cast<const float2*>(base + (static_cast<size_t>(y0) * BW + x1) * nbins));
+    const float2 c10 = __ldg(reinterpret_cast<const float2*>(base + (static_cast<size_t>(y1) * BW + x0) * nbins));
+    const float2 c11 = __ldg(reinterpret_cast<const float2*>(base + (static_cast<size_t>(y1) * BW + x1) * nbins));
     float yv[2], cv[2];
+    cv[0] = (1.f - fy) * ((1.f - fx) * c00.x + fx * c01.x) + fy * ((1.f - fx) * c10.x + fx * c11.x);
+    cv[1] = (1.f - fy) * ((1.f - fx) * c00.y + fx * c01.y) + fy * ((1.f - fx) * c10.y + fx * c11.y);
     float mx = -INFINITY;
 #pragma unroll
     for (int i = 0; i < 2; ++i) {
-      const int k = lane + 32 * i;
       yv[i] = (logc[i] + kf[i] * lp + (Km1 - kf[i]) * lq) * inv_t;
       mx = fmaxf(mx, yv[i]);
-      cv[i] = (1.f - fy) * ((1.f - fx) * __ldg(r00 + k) + fx * __ldg(r01 + k)) +
-              fy * ((1.f - fx) * __ldg(r10 + k) + fx * __ldg(r11 + k));
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
