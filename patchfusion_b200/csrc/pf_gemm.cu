@@ -406,6 +406,25 @@ constexpr int kHaloBytes = kHaloW * kHaloH * 128;          // 23040
 constexpr int kHaloSlot = 24 * 1024;                        // 1024-B aligned slot
 constexpr int kHaloSlots = 3;
 
+// KC consecutive taps (tap0 .. tap0+KC-1) of one 64-channel chunk: 4 MMAs (K = 16 each) per tap.  `tap0` is a
+// literal at every call site, so all A offsets fold to immediates.
+template <int KC>
+__device__ __forceinline__ void issue_taps(uint32_t tmem_d, uint64_t a_hi, uint32_t a_lo, uint64_t b_hi, uint32_t b_lo,
+                                           uint32_t b_tile16, int tap0, uint32_t idesc, uint32_t& first) {
+#pragma unroll
+  for (int j = 0; j < KC; ++j) {
+    const int tap = tap0 + j;
+    const int dy = tap / 3, dx = tap - dy * 3;
+    const uint32_t al = a_lo + ((dy * kHaloW + dx) * 128 >> 4);
+    const uint32_t bl = b_lo + j * b_tile16;
+#pragma unroll
+    for (int k = 0; k < kBlockK / 16; ++k) {
+      umma_bf16(tmem_d, a_hi | (al + 2 * k), b_hi | (bl + 2 * k), idesc, first ? 0u : 1u);
+      first = 0;
+    }
+  }
+}
+
 __global__ void __launch_bounds__(kGemmThreads, 1) pf_conv3_halo_kernel(const __grid_constant__ GemmKernelParams P) {
   extern __shared__ uint8_t smem_raw[];
   const GemmDesc& d = P.d;
@@ -484,28 +503,43 @@ __global__ void __launch_bounds__(kGemmThreads, 1) pf_conv3_halo_kernel(const __
             mbar_wait(&a_full[as], aph);
             tc_fence_after();
             const uint32_t halo = smem_u32(smem + as * kHaloSlot);
-#pragma unroll 1
-            for (int tap0 = 0; tap0 < 9; tap0 += kc) {
+            // Lean single-thread issue loop: descriptors are (constant high word, 32-bit low word); per-tap start
+            // offsets are compile-time immediates in the fully unrolled KC variants.  With small N the MMA itself
+            // costs ~16-64 clk, so every spare instruction in this loop shows up as lost tensor throughput.
+            const uint64_t a_hi = (static_cast<uint64_t>(1) << 46) | (static_cast<uint64_t>(2) << 61) |
+                                  (static_cast<uint64_t>((kHaloW * 128) >> 4) << 32) | (static_cast<uint64_t>(1) << 16);
+            const uint64_t b_hi = (static_cast<uint64_t>(1) << 46) | (static_cast<uint64_t>(2) << 61) |
+                                  (static_cast<uint64_t>(1024 >> 4) << 32) | (static_cast<uint64_t>(1) << 16);
+            const uint32_t a_lo = (halo & 0x3FFFF) >> 4;
+            if (kc == 9) {
               mbar_wait(&b_full[bs], bph);
               tc_fence_after();
-              const uint32_t bstage = smem_u32(smem_b + bs * b_stage_bytes);
-#pragma unroll 1
-              for (int j = 0; j < kc; ++j) {
-                const int tap = tap0 + j;
-                const int dy = tap / 3, dx = tap - dy * 3;
-                // A view: rows (dy*10 + dx) + 10*g + i, g = image row of the tile, i = pixel within the 8-wide row
-                uint64_t adesc = umma_desc_k128(halo + (dy * kHaloW + dx) * 128);
-                adesc = (adesc & ~(static_cast<uint64_t>(0x3FFF) << 32)) |
-                        (static_cast<uint64_t>((kHaloW * 128) >> 4) << 32);
-                const uint64_t bdesc = umma_desc_k128(bstage + j * b_tile_bytes);
-#pragma unroll
-                for (int k = 0; k < kBlockK / 16; ++k) {
-                  umma_bf16(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, first ? 0u : 1u);
-                  first = 0;
-                }
-              }
+              const uint32_t b_lo = (smem_u32(smem_b + bs * b_stage_bytes) & 0x3FFFF) >> 4;
+              issue_taps<9>(tmem_d, a_hi, a_lo, b_hi, b_lo, b_tile_bytes >> 4, 0, idesc, first);
               umma_commit(&b_empty[bs]);
               if (++bs == stages) { bs = 0; bph ^= 1; }
+            } else if (kc == 3) {
+#pragma unroll
+              for (int g = 0; g < 3; ++g) {
+                mbar_wait(&b_full[bs], bph);
+                tc_fence_after();
+                const uint32_t b_lo = (smem_u32(smem_b + bs * b_stage_bytes) & 0x3FFFF) >> 4;
+                if (g == 0) issue_taps<3>(tmem_d, a_hi, a_lo, b_hi, b_lo, b_tile_bytes >> 4, 0, idesc, first);
+                else if (g == 1) issue_taps<3>(tmem_d, a_hi, a_lo, b_hi, b_lo, b_tile_bytes >> 4, 3, idesc, first);
+                else issue_taps<3>(tmem_d, a_hi, a_lo, b_hi, b_lo, b_tile_bytes >> 4, 6, idesc, first);
+                umma_commit(&b_empty[bs]);
+                if (++bs == stages) { bs = 0; bph ^= 1; }
+              }
+            } else {
+#pragma unroll
+              for (int tap = 0; tap < 9; ++tap) {
+                mbar_wait(&b_full[bs], bph);
+                tc_fence_after();
+                const uint32_t b_lo = (smem_u32(smem_b + bs * b_stage_bytes) & 0x3FFFF) >> 4;
+                issue_taps<1>(tmem_d, a_hi, a_lo, b_hi, b_lo, 0, tap, idesc, first);
+                umma_commit(&b_empty[bs]);
+                if (++bs == stages) { bs = 0; bph ^= 1; }
+              }
             }
             umma_commit(&a_empty[as]);                       // halo slot reusable once its 36 MMAs retire
             if (++as == kHaloSlots) { as = 0; aph ^= 1; }
