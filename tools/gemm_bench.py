@@ -14,6 +14,7 @@ SHAPES = [
     ('vit fc1    M7259 K1024 N4096', 'lin', (7259, 1024, 4096)),
     ('vit fc2    M7259 K4096 N1024', 'lin', (7259, 4096, 1024)),
     ('up4.0 3x3 [32,256,256]->544 @392x518 x7', 'conv', (7, 392, 518, [32, 256, 256], 544)),
+    ('up4.0 3x3 [32,256,256]->544 @392x518 x9', 'conv', (9, 392, 518, [32, 256, 256], 544)),
     ('up4.1 3x3 544->32 @392x518 x7', 'conv', (7, 392, 518, [544], 32)),
     ('up3.0 3x3 [256,256,256]->768 @224x296 x7', 'conv', (7, 224, 296, [256, 256, 256], 768)),
     ('up3.1 3x3 768->256 @224x296 x7', 'conv', (7, 224, 296, [768], 256)),
