@@ -181,39 +181,55 @@ __global__ void __launch_bounds__(256) resize_bilinear_tiled_kernel(const bf16* 
                                                                      int OH, int OW, float sy, float sx, int slabs,
                                                                      bf16* __restrict__ out, int out_ld, int out_col0) {
   __shared__ uint4 patch[kRsPH * kRsPW * 8];
-  const int slab = blockIdx.z % slabs, b = blockIdx.z / slabs;
+  __shared__ int s_y0[kRsTH], s_y1[kRsTH];
+  __shared__ float s_fy[kRsTH];
+  const int b = blockIdx.z;
   const int oy0 = blockIdx.y * kRsTH, ox0 = blockIdx.x * kRsTW;
   const int ylo = static_cast<int>(sy * oy0), xlo = static_cast<int>(sx * ox0);
   const int oy1 = min(oy0 + kRsTH, OH) - 1, ox1 = min(ox0 + kRsTW, OW) - 1;
   const int yhi = min(static_cast<int>(sy * oy1) + 1, H - 1), xhi = min(static_cast<int>(sx * ox1) + 1, W - 1);
   const int ph = yhi - ylo + 1, pw = xhi - xlo + 1;          // <= kRsPH x kRsPW for sy, sx <= 1
-  const bf16* base = in + static_cast<size_t>(b) * H * W * in_ld + slab * 64;
-  for (int i = threadIdx.x; i < ph * pw * 8; i += 256) {
-    const int ch = i & 7, pix = i >> 3;
-    const int py = pix / pw, px = pix - py * pw;
-    patch[(py * kRsPW + px) * 8 + ch] =
-        __ldg(reinterpret_cast<const uint4*>(base + (static_cast<size_t>(ylo + py) * W + xlo + px) * in_ld) + ch);
+  // thread -> (16-byte channel chunk, output column); rows of the tile are looped: the x taps are per-thread
+  // constants, the y taps per-row constants shared through smem
+  const int ch = threadIdx.x & 7, tx = threadIdx.x >> 3;
+  const int ox = ox0 + tx;
+  int x0, x1; float fx;
+  ac_coord_s(min(ox, OW - 1), W, sx, x0, x1, fx);
+  x0 -= xlo; x1 -= xlo;
+  if (threadIdx.x < kRsTH) {
+    int y0, y1; float fy;
+    ac_coord_s(min(oy0 + static_cast<int>(threadIdx.x), OH - 1), H, sy, y0, y1, fy);
+    s_y0[threadIdx.x] = y0 - ylo; s_y1[threadIdx.x] = y1 - ylo; s_fy[threadIdx.x] = fy;
   }
-  __syncthreads();
-  for (int i = threadIdx.x; i < kRsTH * kRsTW * 8; i += 256) {
-    const int ch = i & 7, pix = i >> 3;
-    const int ty = pix / kRsTW, tx = pix - ty * kRsTW;
-    const int oy = oy0 + ty, ox = ox0 + tx;
-    if (oy >= OH || ox >= OW) continue;
-    int y0, y1, x0, x1; float fy, fx;
-    ac_coord_s(oy, H, sy, y0, y1, fy);
-    ac_coord_s(ox, W, sx, x0, x1, fx);
-    y0 -= ylo; y1 -= ylo; x0 -= xlo; x1 -= xlo;
-    float a[8], bb[8], c[8], d[8], o[8];
-    unpack8(patch[(y0 * kRsPW + x0) * 8 + ch], a);
-    unpack8(patch[(y0 * kRsPW + x1) * 8 + ch], bb);
-    unpack8(patch[(y1 * kRsPW + x0) * 8 + ch], c);
-    unpack8(patch[(y1 * kRsPW + x1) * 8 + ch], d);
-    const float w00 = (1.f - fy) * (1.f - fx), w01 = (1.f - fy) * fx, w10 = fy * (1.f - fx), w11 = fy * fx;
+  const bf16* base = in + static_cast<size_t>(b) * H * W * in_ld;
+  for (int slab = 0; slab < slabs; ++slab) {
+    __syncthreads();                                         // previous slab's patch fully consumed / tables ready
+    for (int i = threadIdx.x; i < ph * pw * 8; i += 256) {
+      const int c8 = i & 7, pix = i >> 3;
+      const int py = pix / pw, px = pix - py * pw;
+      patch[(py * kRsPW + px) * 8 + c8] = __ldg(reinterpret_cast<const uint4*>(
+          base + (static_cast<size_t>(ylo + py) * W + xlo + px) * in_ld + slab * 64) + c8);
+    }
+    __syncthreads();
+    if (ox < OW) {
+#pragma unroll 2
+      for (int ty = 0; ty < kRsTH; ++ty) {
+        const int oy = oy0 + ty;
+        if (oy >= OH) break;
+        const int y0 = s_y0[ty], y1 = s_y1[ty];
+        const float fy = s_fy[ty];
+        float a[8], bb[8], c[8], d[8], o[8];
+        unpack8(patch[(y0 * kRsPW + x0) * 8 + ch], a);
+        unpack8(patch[(y0 * kRsPW + x1) * 8 + ch], bb);
+        unpack8(patch[(y1 * kRsPW + x0) * 8 + ch], c);
+        unpack8(patch[(y1 * kRsPW + x1) * 8 + ch], d);
+        const float w00 = (1.f - fy) * (1.f - fx), w01 = (1.f - fy) * fx, w10 = fy * (1.f - fx), w11 = fy * fx;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) o[k] = w00 * a[k] + w01 * bb[k] + w10 * c[k] + w11 * d[k];
-    const size_t p = (static_cast<size_t>(b) * OH + oy) * OW + ox;
-    *reinterpret_cast<uint4*>(out + p * out_ld + out_col0 + slab * 64 + ch * 8) = pack8(o);
+        for (int k = 0; k < 8; ++k) o[k] = w00 * a[k] + w01 * bb[k] + w10 * c[k] + w11 * d[k];
+        const size_t p = (static_cast<size_t>(b) * OH + oy) * OW + ox;
+        *reinterpret_cast<uint4*>(out + p * out_ld + out_col0 + slab * 64 + ch * 8) = pack8(o);
+      }
+    }
   }
 }
 
@@ -527,57 +543,79 @@ __global__ void attractor_kernel(const float* __restrict__ A, int A_ld, int nA, 
   }
 }
 
-// one warp per pixel (grid-stride), lane owns the adjacent bins (2*lane, 2*lane+1) so every bilinear tap is one
-// 8-byte load (nbins == 64); the Stirling log C(K-1,k) terms depend on the lane only and are computed once per thread.
+// 8 lanes per pixel (4 pixels per warp, grid-stride), lane j owns bins 8j..8j+7 (two 16-byte loads per bilinear tap,
+// nbins == 64); the Stirling log C(K-1,k) terms depend on the lane only and are computed once per thread; the
+// softmax reductions are 3-step butterflies inside the 8-lane group.
 __global__ void logbinom_depth_kernel(const float* __restrict__ pt, int pt_ld, const float* __restrict__ bc, int BH, int BW,
                                       int B, int H, int W, int nbins, float min_t, float max_t, float sy, float sx,
                                       float* __restrict__ depth) {
-  const int lane = threadIdx.x & 31;
-  const int warps = (gridDim.x * blockDim.x) >> 5;
+  const int lane = threadIdx.x & 31, j = lane & 7;
+  const int groups = (gridDim.x * blockDim.x) >> 3;
   const int total = B * H * W;
   const float Km1 = static_cast<float>(nbins - 1);
-  float logc[2], kf[2];
+  float logc[8];
 #pragma unroll
-  for (int i = 0; i < 2; ++i) {
-    kf[i] = static_cast<float>(2 * lane + i);
-    float n_ = Km1 + 1e-7f, k_ = kf[i] + 1e-7f;
+  for (int i = 0; i < 8; ++i) {
+    float n_ = Km1 + 1e-7f, k_ = static_cast<float>(8 * j + i) + 1e-7f;
     logc[i] = n_ * logf(n_) - k_ * logf(k_) - (n_ - k_) * logf(n_ - k_ + 1e-7f);
   }
   const int hw = H * W;
-  for (int p = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; p < total; p += warps) {
-    const int b = p / hw, rem = p - b * hw;
+  const int iters = (total + groups - 1) / groups;
+  int p = (blockIdx.x * blockDim.x + threadIdx.x) >> 3;
+  for (int it = 0; it < iters; ++it, p += groups) {
+    const bool act = p < total;                  // keep the whole warp in the loop for the shuffles
+    const int pp = act ? p : total - 1;
+    const int b = pp / hw, rem = pp - b * hw;
     const int oy = rem / W, ox = rem - oy * W;
-    const float4 q = __ldg(reinterpret_cast<const float4*>(pt + static_cast<size_t>(p) * pt_ld));
+    const float4 q = __ldg(reinterpret_cast<const float4*>(pt + static_cast<size_t>(pp) * pt_ld));
     float p0 = q.x + 1e-4f, p1 = q.y + 1e-4f, t0 = q.z + 1e-4f, t1 = q.w + 1e-4f;
-    float pr = p0 / (p0 + p1);
-    float tt = t0 / (t0 + t1);
+    float pr = __fdividef(p0, p0 + p1);
+    float tt = __fdividef(t0, t0 + t1);
     tt = (max_t - min_t) * tt + min_t;
     float om = fminf(fmaxf(1.f - pr, 1e-4f), 1.f);
     pr = fminf(fmaxf(pr, 1e-4f), 1.f);
-    const float lp = logf(pr), lq = logf(om), inv_t = 1.f / tt;
+    const float inv_t = __fdividef(1.f, tt);
+    const float lp = __logf(pr) * inv_t, lq = __logf(om) * inv_t;
     int y0, y1, x0, x1; float fy, fx;
     ac_coord_s(oy, BH, sy, y0, y1, fy);
     ac_coord_s(ox, BW, sx, x0, x1, fx);
-    const float* base = bc + static_cast<size_t>(b) * BH * BW * nbins + 2 * lane;
-    const float2 c00 = __ldg(reinterpret_cast<const float2*>(base + (static_cast<size_t>(y0) * BW + x0) * nbins));
-    const float2 c01 = __ldg(reinterpret_cast<const float2*>(base + (static_cast<size_t>(y0) * BW + x1) * nbins));
-    const float2 c10 = __ldg(reinterpret_cast<const float2*>(base + (static_cast<size_t>(y1) * BW + x0) * nbins));
-    const float2 c11 = __ldg(reinterpret_cast<const float2*>(base + (static_cast<size_t>(y1) * BW + x1) * nbins));
-    float yv[2], cv[2];
-    cv[0] = (1.f - fy) * ((1.f - fx) * c00.x + fx * c01.x) + fy * ((1.f - fx) * c10.x + fx * c11.x);
-    cv[1] = (1.f - fy) * ((1.f - fx) * c00.y + fx * c01.y) + fy * ((1.f - fx) * c10.y + fx * c11.y);
+    const float* base = bc + static_cast<size_t>(b) * BH * BW * nbins + 8 * j;
+    const float4* r00 = reinterpret_cast<const float4*>(base + (static_cast<size_t>(y0) * BW + x0) * nbins);
+    const float4* r01 = reinterpret_cast<const float4*>(base + (static_cast<size_t>(y0) * BW + x1) * nbins);
+    const float4* r10 = reinterpret_cast<const float4*>(base + (static_cast<size_t>(y1) * BW + x0) * nbins);
+    const float4* r11 = reinterpret_cast<const float4*>(base + (static_cast<size_t>(y1) * BW + x1) * nbins);
+    const float w00 = (1.f - fy) * (1.f - fx), w01 = (1.f - fy) * fx, w10 = fy * (1.f - fx), w11 = fy * fx;
+    float cv[8], yv[8];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const float4 a = __ldg(r00 + h), bq = __ldg(r01 + h), c = __ldg(r10 + h), d = __ldg(r11 + h);
+      cv[4 * h + 0] = w00 * a.x + w01 * bq.x + w10 * c.x + w11 * d.x;
+      cv[4 * h + 1] = w00 * a.y + w01 * bq.y + w10 * c.y + w11 * d.y;
+      cv[4 * h + 2] = w00 * a.z + w01 * bq.z + w10 * c.z + w11 * d.z;
+      cv[4 * h + 3] = w00 * a.w + w01 * bq.w + w10 * c.w + w11 * d.w;
+    }
     float mx = -INFINITY;
 #pragma unroll
-    for (int i = 0; i < 2; ++i) {
-      yv[i] = (logc[i] + kf[i] * lp + (Km1 - kf[i]) * lq) * inv_t;
+    for (int i = 0; i < 8; ++i) {
+      const float kf = static_cast<float>(8 * j + i);
+      yv[i] = fmaf(logc[i], inv_t, fmaf(kf, lp, (Km1 - kf) * lq));
       mx = fmaxf(mx, yv[i]);
     }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-    float e0 = __expf(yv[0] - mx), e1 = __expf(yv[1] - mx);
-    float den = warp_sum(e0 + e1);
-    float num = warp_sum(e0 * cv[0] + e1 * cv[1]);
-    if (lane == 0) depth[p] = num / den;
+    for (int o = 4; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    float den = 0.f, num = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float e = __expf(yv[i] - mx);
+      den += e;
+      num = fmaf(e, cv[i], num);
+    }
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) {
+      den += __shfl_xor_sync(0xffffffffu, den, o);
+      num += __shfl_xor_sync(0xffffffffu, num, o);
+    }
+    if (act && j == 0) depth[p] = __fdividef(num, den);
   }
 }
 
@@ -680,7 +718,7 @@ int pf_resize_bilinear(const void* in, int32_t B, int32_t H, int32_t W, int32_t 
   const int cg = C / 8;
   const float sy = ac_scale(H, OH), sx = ac_scale(W, OW);
   if (C % 64 == 0 && sy <= 1.0f && sx <= 1.0f && OH * OW >= 4096) {
-    dim3 tgrid((OW + kRsTW - 1) / kRsTW, (OH + kRsTH - 1) / kRsTH, B * (C / 64));
+    dim3 tgrid((OW + kRsTW - 1) / kRsTW, (OH + kRsTH - 1) / kRsTH, B);
     resize_bilinear_tiled_kernel<<<tgrid, 256, 0, ST>>>(static_cast<const bf16*>(in), H, W, in_ld, OH, OW, sy, sx,
                                                         C / 64, static_cast<bf16*>(out), out_ld, out_col0);
     return check_launch("resize_bilinear_tiled_kernel");
