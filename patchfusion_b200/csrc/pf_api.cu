@@ -24,6 +24,10 @@ int set_error(const char* fmt, ...) {
   return 1;
 }
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+bool pdl_enabled() {
+  static const bool on = getenv("PF_B200_PDL") == nullptr || getenv("PF_B200_PDL")[0] != '0';
+  return on;
+}
 int check_launch(const char* what) {
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_error("%s launch: %s", what, cudaGetErrorString(e));

@@ -69,6 +69,7 @@ __global__ void __launch_bounds__(kAttnThreads, 2) pf_attention_kernel(const __g
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tmem_S = tmem_base, tmem_O = tmem_base + 128;
+  pdl_wait();
 
   if (warp == 4) {
     if (lane == 0) {
@@ -259,6 +260,7 @@ extern "C" int pf_attention(const void* qk, int32_t qk_ld, const void* vt, int32
   P.out = static_cast<__nv_bfloat16*>(out);
   P.out_ld = out_ld;
   dim3 grid((seq + kQTile - 1) / kQTile, heads, B);
-  pf_attention_kernel<<<grid, kAttnThreads, smem_bytes, static_cast<cudaStream_t>(stream)>>>(P);
+  cudaError_t le = launch_pdl(pf_attention_kernel, grid, dim3(kAttnThreads), smem_bytes, static_cast<cudaStream_t>(stream), P);
+  if (le != cudaSuccess) return set_error("pf_attention_kernel launch: %s", cudaGetErrorString(le));
   return check_launch("pf_attention_kernel");
 }

@@ -62,6 +62,7 @@ __device__ __forceinline__ void ln_row(const float* __restrict__ xr, const float
 __global__ void layernorm_kernel(const float* __restrict__ x, int x_ld, const float* __restrict__ w,
                                  const float* __restrict__ b, float eps, int rows, int C, bf16* __restrict__ out,
                                  int out_ld) {
+  pdl_wait();
   int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
   ln_row(x + static_cast<long long>(row) * x_ld, w, b, eps, C, out + static_cast<long long>(row) * out_ld,
@@ -689,7 +690,9 @@ extern "C" {
 int pf_layernorm(const float* x, int32_t x_ld, const float* w, const float* b, float eps, int32_t rows, int32_t C,
                  void* out, int32_t out_ld, void* stream) {
   if (C % 4 || x_ld % 4 || out_ld % 4 || C > 1024) return set_error("pf_layernorm: C (<= 1024) and strides must be multiples of 4");
-  layernorm_kernel<<<nblocks(rows, 8), 256, 0, ST>>>(x, x_ld, w, b, eps, rows, C, static_cast<bf16*>(out), out_ld);
+  cudaError_t le = launch_pdl(layernorm_kernel, dim3(nblocks(rows, 8)), dim3(256), 0, ST, x, x_ld, w, b, eps, rows, C,
+                              static_cast<bf16*>(out), out_ld);
+  if (le != cudaSuccess) return set_error("layernorm_kernel launch: %s", cudaGetErrorString(le));
   return check_launch("layernorm_kernel");
 }
 

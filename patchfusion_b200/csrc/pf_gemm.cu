@@ -310,6 +310,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) pf_gemm_kernel(const __grid_c
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  pdl_launch_dependents();          // persistent kernel, all CTAs resident: let the next kernel's prologue start
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < d.num_src; ++s) prefetch_tmap(&P.tmA[s]);
@@ -323,6 +324,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) pf_gemm_kernel(const __grid_c
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();                       // predecessor's results are visible from here on
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -446,6 +448,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) pf_conv3_halo_kernel(const __
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  pdl_launch_dependents();
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < d.num_src; ++s) prefetch_tmap(&P.tmA[s]);
     prefetch_tmap(&P.tmB);
@@ -459,6 +462,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) pf_conv3_halo_kernel(const __
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();                       // predecessor's results are visible from here on
 
   if (warp == 0) {
     if (lane == 0) {
@@ -616,9 +620,11 @@ int gemm_launch(const GemmDesc& d, const CUtensorMap* tmA, const CUtensorMap& tm
     if (hstages < 2) return set_error("conv3 halo: not enough shared memory");
     P.stages = hstages;
     size_t hsmem = 1024 + static_cast<size_t>(kHaloSlots) * kHaloSlot + static_cast<size_t>(hstages) * b_bytes + kTailBytes;
-    pf_conv3_halo_kernel<<<grid, kGemmThreads, hsmem, stream>>>(P);
+    cudaError_t le = launch_pdl(pf_conv3_halo_kernel, dim3(grid), dim3(kGemmThreads), hsmem, stream, P);
+    if (le != cudaSuccess) return set_error("pf_conv3_halo_kernel launch: %s", cudaGetErrorString(le));
   } else {
-    pf_gemm_kernel<<<grid, kGemmThreads, smem, stream>>>(P);
+    cudaError_t le = launch_pdl(pf_gemm_kernel, dim3(grid), dim3(kGemmThreads), smem, stream, P);
+    if (le != cudaSuccess) return set_error("pf_gemm_kernel launch: %s", cudaGetErrorString(le));
   }
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_error("pf_gemm_kernel launch: %s", cudaGetErrorString(e));
