@@ -25,7 +25,8 @@ int set_error(const char* fmt, ...) {
 }
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 bool pdl_enabled() {
-  static const bool on = getenv("PF_B200_PDL") == nullptr || getenv("PF_B200_PDL")[0] != '0';
+  // opt-in (PF_B200_PDL=1): measured neutral inside CUDA graphs on B200, so the default stays the plain launch
+  static const bool on = getenv("PF_B200_PDL") != nullptr && getenv("PF_B200_PDL")[0] == '1';
   return on;
 }
 int check_launch(const char* what) {

@@ -111,7 +111,6 @@ class Engine:
             Wd['clb.0'] = ops.pack_weight(w0, b0, src_c=[32, E])
         else:
             Wd['clb.0'] = ops.pack_weight(w0, b0, src_c=[32, 1, E])
-        Wd['clb.2'] = self._conv(pre + 'conditional_log_binomial.mlp.2')
         Wd['clb.tail'] = (self._w(pre + 'conditional_log_binomial.mlp.2.weight').reshape(4, -1).float().contiguous(),
                           self._f32(pre + 'conditional_log_binomial.mlp.2.bias'))
         return Wd
@@ -167,7 +166,6 @@ class Engine:
                 Wd['ff%d.u%d.c2' % (i, u)] = self._conv(r + 'resConfUnit%d.conv2' % u)
         Wd['oc1'] = self._conv(dh + 'scratch.output_conv1')
         Wd['oc2.0'] = self._conv(dh + 'scratch.output_conv2.0')
-        Wd['oc2.2'] = self._conv(dh + 'scratch.output_conv2.2')
         Wd['oc2.tail'] = (self._w(dh + 'scratch.output_conv2.2.weight').reshape(1, -1).float().contiguous(),
                           self._f32(dh + 'scratch.output_conv2.2.bias'))
         Wd['conv2'] = self._conv(pre + 'conv2')

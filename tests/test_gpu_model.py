@@ -234,3 +234,53 @@ def test_vitl_full_size_tile_against_oracle(cuda):
     out = torch.empty_like(n2)
     ops.call('pf_stitch_finalize', n2, d2, ops.C.c_int64(n2.numel()), out, ops.stream_ptr())
     assert (out - 3.25).abs().max().item() < 1e-5
+
+
+def _cuda_oracle(cfg, sd, cuda):
+    from oracle import pf_oracle as po
+    return po, po.Oracle({k: v.to(cuda) for k, v in sd.items()}, cfg)
+
+
+def test_tile_cfg_override_4x4_and_r_mode(cuda, setup):
+    """`tile_cfg=` override (patchfusion.py:402-405): 16 + random tiles on a 4x4 split of the 1080p image, against the
+    oracle executed by torch on the GPU (fp32, TF32 off)."""
+    s = setup
+    model, img = s['model'], s['img'].to(cuda)
+    po, orc = _cuda_oracle(s['cfg'], s['sd'], cuda)
+    lr = orc.resizer(img)
+    tcfg = {'image_raw_shape': [1080, 1920], 'patch_split_num': [4, 4]}
+    for mode, pn in (('m1', 4), ('r8', 4)):
+        random.seed(1)
+        with torch.no_grad():
+            want = orc.infer(lr, img, tile_cfg=tcfg, cai_mode=mode, process_num=pn)
+        random.seed(1)
+        got, _ = model(mode='infer', image_lr=lr, image_hr=img, tile_cfg=tcfg, cai_mode=mode, process_num=pn)
+        assert got.shape == want.shape
+        err = (got - want).abs().max().item()
+        print('%s 4x4: max-abs %.3e (range %.3f..%.3f)' % (mode, err, want.min().item(), want.max().item()))
+        assert err / MAX_DEPTH < 1e-3 and err / (want.max() - want.min()).item() < 5e-2
+    with pytest.raises(AssertionError):
+        model(mode='infer', image_lr=lr, image_hr=img, tile_cfg={'image_raw_shape': [1080, 1920], 'patch_split_num': [7, 4]})
+
+
+def test_vitb_branch(cuda):
+    """Depth-Anything-vitb (BASELINE.json configs[4] encoder: dim 768, 12 heads, features 128): one branch forward of
+    two tiles against the GPU-executed oracle."""
+    from patchfusion_b200.configs import depth_anything_patchfusion
+    from patchfusion_b200.model import PatchFusion
+    from patchfusion_b200.params import synthetic_state_dict
+    cfg = depth_anything_patchfusion('vitb')
+    sd = synthetic_state_dict(cfg, seed=2)
+    model = PatchFusion(cfg)
+    model.load_state_dict(sd, strict=True)
+    model = model.to(cuda).eval()
+    po, orc = _cuda_oracle(cfg, sd, cuda)
+    x = torch.rand(2, 3, 392, 518, generator=torch.Generator().manual_seed(5)).to(cuda)
+    with torch.no_grad():
+        d_o, f_o = po.branch_forward(orc.sd, 'fine_branch.', x, cfg['fine_branch'])
+    d, f = model.engine().branch('fine', x.contiguous())
+    for a, b in zip(f, f_o):
+        assert rel_err(a.t[..., :a.C].float().permute(0, 3, 1, 2), b) < 3e-2
+    err = (d - d_o[:, 0]).abs().max().item()
+    print('vitb fine depth max-abs %.3e (range %.3f..%.3f)' % (err, d_o.min().item(), d_o.max().item()))
+    assert err / MAX_DEPTH < 1e-3 and err / (d_o.max() - d_o.min()).item() < 5e-2
