@@ -14,7 +14,6 @@ import os
 import subprocess
 import sys
 import tempfile
-import threading
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -188,7 +187,7 @@ def main():
             gpu_launches=0)))
         return
 
-    from patchfusion_b200 import lib, ops
+    from patchfusion_b200 import lib
     from patchfusion_b200.model import PatchFusion
     dev = torch.device('cuda', local)
     torch.cuda.set_device(dev)

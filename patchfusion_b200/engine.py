@@ -16,13 +16,12 @@ one-off load-time transforms (pos-embed bicubic resample, BatchNorm folding cons
 import ctypes as ct
 import math
 
-import numpy as np
 import torch
 import torch.nn.functional as F
 
 from . import ops
 from .ops import ACT_GELU, ACT_NONE, ACT_RELU, ACT_SOFTPLUS, call, pad_to, stream_ptr
-from .params import ENCODERS, G2L_DEPTH, G2L_HEADS, WINDOW, branch_hparams, guided_fusion_hparams, _get
+from .params import WINDOW, branch_hparams, guided_fusion_hparams, _get
 
 BF16, F32 = torch.bfloat16, torch.float32
 

@@ -4,7 +4,6 @@ Tensors are torch CUDA tensors used as typed device buffers: activations bf16 NH
 channel count tracked by the caller), token matrices `[rows, ld]`, fp32 where include/pf_b200.h says so.
 """
 import ctypes as C
-import math
 
 import torch
 
