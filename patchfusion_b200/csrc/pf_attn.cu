@@ -140,7 +140,9 @@ __global__ void __launch_bounds__(kAttnThreads, 2) pf_attention_kernel(const __g
       tc_fence_after();
       // pass 1: row max of the raw scores (scale > 0, applied once afterwards).  TMEM loads are software
       // pipelined: chunk i+1 is in flight while chunk i is consumed.
-      float m_raw = -INFINITY;
+      // four independent max / sum chains: the serial 128-long FMNMX / FADD dependency chains were the critical
+      // path of a softmax warp (2 warps per scheduler cannot hide 4-cycle-latency chains)
+      float mr[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
       const bool full = kvalid == kKTile;
       uint32_t va[32], vb[32];
       tmem_ld32(tmem_S + lane_sel, va);
@@ -154,17 +156,18 @@ __global__ void __launch_bounds__(kAttnThreads, 2) pf_attention_kernel(const __g
         const int cb = c2 * 32;
         if (full) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) m_raw = fmaxf(m_raw, __uint_as_float(cur[i]));
+          for (int i = 0; i < 32; ++i) mr[i & 3] = fmaxf(mr[i & 3], __uint_as_float(cur[i]));
         } else {
 #pragma unroll
           for (int i = 0; i < 32; ++i)
-            if (cb + i < kvalid) m_raw = fmaxf(m_raw, __uint_as_float(cur[i]));
+            if (cb + i < kvalid) mr[i & 3] = fmaxf(mr[i & 3], __uint_as_float(cur[i]));
         }
         tmem_ld_wait();
       }
+      const float m_raw = fmaxf(fmaxf(mr[0], mr[1]), fmaxf(mr[2], mr[3]));
       const float m_new = fmaxf(m_run, m_raw * P.scale_log2);
       const float alpha = ex2_approx(m_run - m_new);
-      float l_blk = 0.0f;
+      float ls[4] = {0.f, 0.f, 0.f, 0.f};
       // pass 2: p = 2^(s*scale - m) (one FFMA + one MUFU per score), bf16 pairs -> swizzled smem tile.
       // (va holds chunk 0 again at this point)
 #pragma unroll
@@ -178,14 +181,14 @@ __global__ void __launch_bounds__(kAttnThreads, 2) pf_attention_kernel(const __g
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
             p[i] = ex2_approx(fmaf(__uint_as_float(cur[i]), P.scale_log2, -m_new));
-            l_blk += p[i];
+            ls[i & 3] += p[i];
           }
         } else {
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
             float e = ex2_approx(fmaf(__uint_as_float(cur[i]), P.scale_log2, -m_new));
             p[i] = (cb + i < kvalid) ? e : 0.0f;
-            l_blk += p[i];
+            ls[i & 3] += p[i];
           }
         }
         uint8_t* sub = sP + (cb >> 6) * 16384 + r * 128;
@@ -198,7 +201,7 @@ __global__ void __launch_bounds__(kAttnThreads, 2) pf_attention_kernel(const __g
         }
         if (c2 + 1 < kKTile / 32) tmem_ld_wait();
       }
-      l_run = l_run * alpha + l_blk;
+      l_run = l_run * alpha + ((ls[0] + ls[1]) + (ls[2] + ls[3]));
       m_run = m_new;
       fence_proxy_async_smem();      // generic-proxy smem writes -> visible to the tensor core (async proxy)
       tc_fence_before();
