@@ -166,6 +166,8 @@ def main():
     rank = int(os.environ.get('RANK', 0))
     world = int(os.environ.get('WORLD_SIZE', 1))
     local = int(os.environ.get('LOCAL_RANK', 0))
+    # torchrun pins OMP_NUM_THREADS=1: give the host-side weight synthesis / packing a fair share of the cores
+    torch.set_num_threads(max(1, min(16, (os.cpu_count() or 8) // max(world, 1))))
     enc = args.encoder
     n_tiles = {'m1': 16, 'm2': 49}[args.cai_mode]
     workload = 'Depth-Anything-%s PatchFusion, 4K (2160x3840), P%d (%s, 4x4 split), %d image/rank/step' % (
