@@ -324,7 +324,7 @@ def main():
                                                                          v['flops'] / max(v['ms'], 1e-9) / 1e9))
     cb = None
     if not args.no_cpu_baseline and world == 1:
-        cb = cpu_baseline(enc, cfg, sd)
+        cb = cpu_baseline(enc, cfg, sd, reps=1, warm=1)
     out = dict(
         metric='tiles/s', value=tps, unit='tiles/s', n_gpus=world, steps=args.steps, warmup=max(args.warmup, 3),
         ms_per_step=ms_dev / args.steps, higher_is_better=True, scaling='weak', vs_baseline=None, dtype='bf16',
