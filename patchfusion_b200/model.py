@@ -213,6 +213,50 @@ class PatchFusion(ParamTree, PyTorchModelHubMixin):
         d, feats = self.engine().branch('fine', image_hr_crop.float().contiguous())
         return d[:, None].clone(), [self._nchw(f) for f in feats]
 
+    def _to_map(self, x):
+        """NCHW fp32 tensor -> engine Map (NHWC bf16, channels padded to 8)."""
+        from .engine import Map
+        from .ops import pad_to
+        B, C, H, W = x.shape
+        t = torch.zeros((B, H, W, pad_to(C, 8)), dtype=torch.bfloat16, device=x.device)
+        t[..., :C] = x.permute(0, 2, 3, 1).to(torch.bfloat16)
+        return Map(t, C)
+
+    @torch.no_grad()
+    def coarse_postprocess_test(self, coarse_prediction, coarse_features, bboxs, bboxs_feat):
+        """`patchfusion.py:240-257`: ROI crop-zoom of the coarse depth and taps for the boxes `bboxs_feat` (T,5:
+        batch index, x1, y1, x2, y2 in patch_process units).  NCHW fp32 in / out like the reference."""
+        from . import ops
+        boxes = bboxs_feat[:, 1:].float().contiguous()
+        T = boxes.shape[0]
+        P = self.patch_process_shape
+        feats = []
+        for f in coarse_features:
+            m = self._to_map(f.float())
+            h, w = m.hw
+            out = torch.zeros((T, h, w, m.t.shape[-1]), dtype=torch.bfloat16, device=f.device)
+            ops.roi_crop_zoom(m.t, m.C, boxes, h / P[0], out)
+            feats.append(out[..., :m.C].float().permute(0, 3, 1, 2).contiguous())
+        d = coarse_prediction.float().contiguous()
+        droi = torch.zeros((T,) + tuple(d.shape[-2:]), dtype=torch.float32, device=d.device)
+        ops.roi_crop_zoom(d[0, 0].contiguous(), 1, boxes, d.shape[-2] / P[0], droi)
+        return {'coarse_depth_roi': droi[:, None], 'coarse_feats_roi': feats}
+
+    @torch.no_grad()
+    def infer_forward(self, imgs_crop, bbox_feat_forward, tile_temp, coarse_temp_dict=None):
+        """`patchfusion.py:343-356`: fine branch + guided fusion of the given crops (T,3,h,w in [0,1]) against the
+        whole-image coarse outputs in `tile_temp` ({'coarse_prediction', 'coarse_features'}, NCHW fp32).  As in the
+        reference the G2L maps are recomputed from `tile_temp` on every call; `coarse_temp_dict` (the precomputed ROI
+        crops) is accepted for signature compatibility - the kernels re-derive the crops from the boxes."""
+        eng = self.engine()
+        crops = imgs_crop.float().contiguous()
+        boxes = bbox_feat_forward[:, 1:].float().contiguous()
+        cf = [self._to_map(f.float()) for f in tile_temp['coarse_features']]
+        cd = tile_temp['coarse_prediction'].float()[0, 0].contiguous()
+        g2l = eng.g2l(cf)
+        fd, ff = eng.branch('fine', crops)
+        return eng.fusion(crops, boxes, fd, ff, cd, cf, g2l)[:, None].clone()
+
     # ------------------------------------------------------------------ tiling
     def _graphed(self, key, fn):
         """Run `fn` (a fixed kernel sequence over static buffers) through a CUDA graph: first call runs eagerly

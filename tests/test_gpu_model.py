@@ -284,3 +284,33 @@ def test_vitb_branch(cuda):
     err = (d - d_o[:, 0]).abs().max().item()
     print('vitb fine depth max-abs %.3e (range %.3f..%.3f)' % (err, d_o.min().item(), d_o.max().item()))
     assert err / MAX_DEPTH < 1e-3 and err / (d_o.max() - d_o.min()).item() < 5e-2
+
+
+def test_stage_level_api(cuda, setup):
+    """Reference-named stage entry points (coarse_forward / coarse_postprocess_test / infer_forward, NCHW fp32 in and
+    out) reproduce the tile result of the fused path and torchvision's roi_align."""
+    from torchvision.ops import roi_align
+    s = setup
+    model, img = s['model'], s['img'].to(cuda)
+    lr = model.resizer(img)
+    cd, cf = model.coarse_forward(lr)
+    assert cd.shape == (1, 1, 392, 518) and [tuple(f.shape[-2:]) for f in cf][0] == (14, 19)
+    H, W = s['case']['image_raw_shape']
+    h, w = H // 2, W // 2
+    raw = [(0, 0), (h // 2, w // 2)]
+    P = s['cfg']['patch_process_shape']
+    fx, fy = 1 / W * P[1], 1 / H * P[0]
+    bf5 = torch.tensor([[0, x * fx, y * fy, (x + w) * fx, (y + h) * fy] for (y, x) in raw], device=cuda)
+    post = model.coarse_postprocess_test(cd, cf, None, bf5)
+    ref = roi_align(cf[3], bf5, cf[3].shape[-2:], cf[3].shape[-2] / P[0], aligned=True)
+    assert rel_err(post['coarse_feats_roi'][3], ref) < 1e-2
+    refd = roi_align(cd, bf5, (392, 518), 1.0, aligned=True)
+    assert (post['coarse_depth_roi'] - refd).abs().max().item() < 1e-5
+    crops = torch.cat([model.resizer(img[:, :, y:y + h, x:x + w]) for (y, x) in raw])
+    pred = model.infer_forward(crops, bf5, {'coarse_prediction': cd, 'coarse_features': cf}, post)
+    assert pred.shape == (2, 1, 392, 518)
+    want = torch.tensor(s['gold']['fusion_depth'])
+    st = s['case']['sample_stride']
+    err = (pred.cpu()[..., ::st, ::st] - want).abs().max().item()
+    print('infer_forward vs reference fixture max-abs %.3e' % err)
+    assert err / MAX_DEPTH < 1e-3
