@@ -189,6 +189,11 @@ def main():
             gpu_launches=0)))
         return
 
+    # keep stdout clean for the single JSON line: libraries (NCCL's version banner, ...) that write to fd 1 during
+    # the run are sent to stderr; the descriptor is restored right before the result is printed
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
     from patchfusion_b200 import lib
     from patchfusion_b200.model import PatchFusion
     dev = torch.device('cuda', local)
@@ -334,7 +339,9 @@ def main():
         e2e=dict(value=tps_e2e, unit='tiles/s', h2d_bytes_per_step=host_img.numel() * 4,
                  d2h_bytes_per_step=host_out.numel() * 4),
         gpu_launches=launches, clocks=clocks, roofline=roof, cpu_baseline=cb)
-    print(json.dumps(out))
+    sys.stdout.flush()
+    os.dup2(saved_stdout, 1)
+    print(json.dumps(out), flush=True)
 
 
 if __name__ == '__main__':
