@@ -133,6 +133,16 @@ int pf_pack_unet_input(const float* coarse_depth_roi, const float* fine_depth, c
 /* tokens [B, n, D] bf16 rows -> skip cls handled by caller; generic strided row copy / convert helpers */
 int pf_f32_to_bf16(const float* in, int64_t n, void* out, void* stream);
 
+/* ---- callers either side of the path ------------------------------------------------- */
+/* uint8 HWC image (bgr != 0: cv2.imread channel order) -> planar RGB fp32 in [0,1] resized with bicubic
+ * align_corners=True to (OH, OW): estimator/datasets/general_dataset.py:40-45. */
+int pf_ingest_u8(const uint8_t* img_hwc, int32_t H, int32_t W, int32_t bgr, int32_t OH, int32_t OW, float* out_planar,
+                 void* stream);
+/* depth canvas -> uint16: nearest resize to (OH, OW) (tools/test_single_forward.py:26) then saturating
+ * (depth * scale) cast (estimator/tester/tester.py:75-76, scale 256). */
+int pf_depth_to_u16(const float* depth, int32_t H, int32_t W, int32_t OH, int32_t OW, float scale, uint16_t* out,
+                    void* stream);
+
 /* ---- Swin / G2L (estimator/models/blocks/swin_layers.py) ------------------------------------------------------ */
 /* x[h*w, C] fp32 = NHWC bf16 feature + absolute_pos_embed (swin_layers.py:419-422) */
 int pf_g2l_embed(const void* feat, int32_t feat_ld, const float* ape, int32_t n, int32_t C, float* x, void* stream);

@@ -387,6 +387,55 @@ __global__ void pack_unet_input_kernel(const float* __restrict__ cd, const float
   *reinterpret_cast<uint4*>(out + p * ld) = pack8(f);
 }
 
+// ------------------------------------------------------------------------------------------------ image ingest / output
+// (the callers either side of the hot path)
+// uint8 HWC (BGR as cv2.imread returns it, or RGB) -> planar RGB fp32 in [0,1], bicubic (A = -0.75, align_corners=True,
+// border taps clamped) to (OH, OW): `estimator/datasets/general_dataset.py:40-45` (cv2 decode -> /255 -> F.interpolate).
+__device__ __forceinline__ float cubic1(float x, float A) { return ((A + 2.f) * x - (A + 3.f)) * x * x + 1.f; }
+__device__ __forceinline__ float cubic2(float x, float A) { return ((A * x - 5.f * A) * x + 8.f * A) * x - 4.f * A; }
+
+__global__ void ingest_u8_kernel(const uint8_t* __restrict__ img, int H, int W, int bgr, int OH, int OW, float sy, float sx,
+                                 float* __restrict__ out) {
+  const int ox = blockIdx.x * blockDim.x + threadIdx.x, oy = blockIdx.y;
+  if (ox >= OW) return;
+  const float A = -0.75f;
+  const float ry = sy * oy, rx = sx * ox;
+  const int iy = static_cast<int>(floorf(ry)), ix = static_cast<int>(floorf(rx));
+  const float ty = ry - iy, tx = rx - ix;
+  const float wy[4] = {cubic2(ty + 1.f, A), cubic1(ty, A), cubic1(1.f - ty, A), cubic2(2.f - ty, A)};
+  const float wx[4] = {cubic2(tx + 1.f, A), cubic1(tx, A), cubic1(1.f - tx, A), cubic2(2.f - tx, A)};
+  float acc[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+  for (int a = 0; a < 4; ++a) {
+    const int yy = min(max(iy - 1 + a, 0), H - 1);
+    float row[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      const int xx = min(max(ix - 1 + b, 0), W - 1);
+      const uint8_t* px = img + (static_cast<size_t>(yy) * W + xx) * 3;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) row[c] += wx[b] * (static_cast<float>(px[c]) * (1.0f / 255.0f));
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) acc[c] += wy[a] * row[c];
+  }
+  const size_t plane = static_cast<size_t>(OH) * OW, o = static_cast<size_t>(oy) * OW + ox;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) out[(bgr ? 2 - c : c) * plane + o] = acc[c];
+}
+
+// depth canvas -> uint16 image: nearest resize (F.interpolate default, `tools/test_single_forward.py:26`) then
+// (depth * scale).astype(uint16) as `estimator/tester/tester.py:75-76` (scale 256), saturating.
+__global__ void depth_to_u16_kernel(const float* __restrict__ d, int H, int W, int OH, int OW, float scale,
+                                    uint16_t* __restrict__ out) {
+  const int ox = blockIdx.x * blockDim.x + threadIdx.x, oy = blockIdx.y;
+  if (ox >= OW) return;
+  const int sy = min(static_cast<int>(floorf(oy * (static_cast<float>(H) / OH))), H - 1);
+  const int sx = min(static_cast<int>(floorf(ox * (static_cast<float>(W) / OW))), W - 1);
+  const float v = d[static_cast<size_t>(sy) * W + sx] * scale;
+  out[static_cast<size_t>(oy) * OW + ox] = static_cast<uint16_t>(fminf(fmaxf(v, 0.f), 65535.f));
+}
+
 // ------------------------------------------------------------------------------------------------ Swin / G2L
 __global__ void g2l_embed_kernel(const bf16* __restrict__ feat, int feat_ld, const float* __restrict__ ape, int n, int C,
                                  float* __restrict__ x) {
@@ -786,6 +835,20 @@ int pf_pack_unet_input(const float* coarse_depth_roi, const float* fine_depth, c
   pack_unet_input_kernel<<<nblocks(total, 256), 256, 0, ST>>>(coarse_depth_roi, fine_depth, rgb_planar, T, H, W,
                                                                static_cast<bf16*>(out), ld);
   return check_launch("pack_unet_input_kernel");
+}
+
+int pf_ingest_u8(const uint8_t* img_hwc, int32_t H, int32_t W, int32_t bgr, int32_t OH, int32_t OW, float* out_planar,
+                 void* stream) {
+  dim3 grid(nblocks(OW, 256), OH);
+  ingest_u8_kernel<<<grid, 256, 0, ST>>>(img_hwc, H, W, bgr, OH, OW, ac_scale(H, OH), ac_scale(W, OW), out_planar);
+  return check_launch("ingest_u8_kernel");
+}
+
+int pf_depth_to_u16(const float* depth, int32_t H, int32_t W, int32_t OH, int32_t OW, float scale, uint16_t* out,
+                    void* stream) {
+  dim3 grid(nblocks(OW, 256), OH);
+  depth_to_u16_kernel<<<grid, 256, 0, ST>>>(depth, H, W, OH, OW, scale, out);
+  return check_launch("depth_to_u16_kernel");
 }
 
 int pf_g2l_embed(const void* feat, int32_t feat_ld, const float* ape, int32_t n, int32_t C, float* x, void* stream) {

@@ -222,3 +222,20 @@ def test_stitch(cuda):
     a3[100:100 + uh, 333:333 + uw] = upd * mask2
     ra.update(a3, c3)
     check('stitch (resize + random tile)', out2, ra.avg, 1e-5)
+
+
+def test_ingest_and_u16_writer(cuda):
+    """the callers either side of the path: bicubic align_corners ingest and the uint16 depth writer"""
+    from patchfusion_b200 import imageio
+    g = torch.Generator().manual_seed(9)
+    img = torch.randint(0, 256, (270, 480, 3), generator=g, dtype=torch.uint8)
+    got = imageio.ingest(img.numpy(), (1080, 1920), cuda, bgr=True)
+    rgb = img.numpy()[:, :, ::-1].copy()
+    ref = F.interpolate(torch.tensor(rgb / 255.0).unsqueeze(0).permute(0, 3, 1, 2), (1080, 1920), mode='bicubic',
+                        align_corners=True).float()
+    assert got.shape == (1, 3, 1080, 1920)
+    assert (got.cpu() - ref).abs().max().item() < 1e-4
+    d = torch.rand(784, 1036, generator=g) * 80
+    u = imageio.depth_to_u16(d.to(cuda)[None, None], (1080, 1920))
+    want = (F.interpolate(d[None, None], (1080, 1920))[0, 0].numpy() * 256).astype('uint16')
+    assert u.dtype == torch.uint16 and (u.cpu().numpy().astype(np.int64) - want.astype(np.int64)).__abs__().max() <= 1
