@@ -104,6 +104,7 @@ static int encode(CUtensorMap* out, const void* ptr, int rank, const uint64_t* d
                      rank > 1 ? box[1] : 0, rank > 2 ? box[2] : 0, rank > 3 ? box[3] : 0);
   }
   std::lock_guard<std::mutex> g(g_maps_mu);
+  if (g_maps.size() > 65536) g_maps.clear();      // callers with ever-changing pointers: bound the cache
   g_maps.emplace(key, *out);
   return 0;
 }
