@@ -65,3 +65,17 @@ def test_no_fallback_when_library_missing(monkeypatch, tmp_path):
     monkeypatch.setattr(lib, 'LIB_PATH', str(tmp_path / 'nope.so'))
     with pytest.raises(lib.PFError):
         lib.load()
+
+
+def test_ctypes_signatures_match_header_arity():
+    """every `int pf_*(...)` prototype in include/pf_b200.h is bound in lib.SIGNATURES with the same arity"""
+    from patchfusion_b200 import lib
+    src = re.sub(r'/\*.*?\*/', '', open(HDR).read(), flags=re.S)
+    protos = re.findall(r'\bint\s+(pf_[A-Za-z0-9_]+)\s*\(([^;{]*?)\)\s*;', src, flags=re.S)
+    assert len(protos) >= 25
+    for name, args in protos:
+        if name == 'pf_version':
+            continue
+        n = 0 if args.strip() == 'void' else len(args.split(','))
+        assert name in lib.SIGNATURES, name
+        assert n == len(lib.SIGNATURES[name]), (name, n, len(lib.SIGNATURES[name]))
