@@ -5,8 +5,10 @@
     python bench.py --impl reference ...                               (reference algorithm on the host cores)
 
 A step = one pass of the hot path over one synthetic 4K image per rank: coarse branch + G2L once, 49 tiles through
-fine branch + guided fusion, scatter-stitch.  Ranks process independent images (weak scaling) and one NCCL
-all-gather assembles the batch of depth canvases.  Prints ONE JSON line (rank 0).
+fine branch + guided fusion, stitch.  `value`: ranks process independent images (weak scaling, no data-path
+collective).  `tile_sharded`: a second timed region where ONE image's tiles are sharded over the ranks with a single
+NCCL all-gather of the per-rank prediction blocks (strong scaling of one image, BASELINE configs[2]).
+Prints ONE JSON line (rank 0).
 """
 import argparse
 import json
@@ -87,58 +89,131 @@ def build_inputs(encoder, seed=0):
     return cfg, sd
 
 
-def pick_threads():
-    """torch CPU kernels stop scaling (and regress) well before 128 threads on these hosts: time one 3x3 conv and one
-    matmul of the path's sizes at a few thread counts and keep the fastest (<= all cores)."""
-    import torch.nn.functional as F
-    n = os.cpu_count()
-    x = torch.randn(1, 256, 224, 296)
-    w = torch.randn(256, 256, 3, 3)
-    a = torch.randn(1037, 1024)
-    b = torch.randn(1024, 4096)
-    best, best_t = n, None
-    for t in sorted(set([min(n, c) for c in (8, 16, 32, 64, n)])):
-        torch.set_num_threads(t)
-        with torch.no_grad():
-            F.conv2d(x, w, padding=1)
-            t0 = time.time()
-            F.conv2d(x, w, padding=1)
-            a @ b
-            dt = time.time() - t0
-        if best_t is None or dt < best_t:
-            best, best_t = t, dt
-    return best
-
-
-def cpu_baseline(encoder, cfg, sd, threads=None, reps=1, warm=0):
-    """The oracle (a port of the reference algorithm) on the host cores: micro-batches of ONE tile (fine branch +
-    fusion) after the per-image fixed work; bounded sample, not the product path."""
+def _cpu_tile_runner(encoder, cfg, sd):
+    """oracle state for timing single tiles of the 4K P49 workload on the host (fixed per-image work done once)."""
     from oracle import pf_oracle as po
-    threads = threads or pick_threads()
-    torch.set_num_threads(threads)
     g = torch.Generator().manual_seed(1)
     img = torch.rand(1, 3, 2160, 3840, generator=g)
     orc = po.Oracle(sd, cfg)
     P = cfg['patch_process_shape']
-    with torch.no_grad():
-        lr = orc.resizer(img)
-        t0 = time.time()
-        cd, cf = orc.coarse(lr)
-        g2l = po.g2l_all(sd, cf, cfg['guided_fusion'])
-        t_fixed = time.time() - t0
-        tc = po.prepare_tile_cfg((2160, 3840), (4, 4), P)
-        ts = []
-        for r in range(warm + reps):
+    tc = po.prepare_tile_cfg((2160, 3840), (4, 4), P)
+    st = {}
+
+    def fixed():
+        with torch.no_grad():
+            lr = orc.resizer(img)
             t0 = time.time()
-            orc.tiles(img, [(540 * (r % 4), 960)], cd, cf, g2l, 1, tc)
-            if r >= warm:
-                ts.append(time.time() - t0)
+            st['cd'], st['cf'] = orc.coarse(lr)
+            st['g2l'] = po.g2l_all(sd, st['cf'], cfg['guided_fusion'])
+            return time.time() - t0
+
+    def tile(r):
+        with torch.no_grad():
+            t0 = time.time()
+            orc.tiles(img, [(540 * (r % 4), 960)], st['cd'], st['cf'], st['g2l'], 1, tc)
+            return time.time() - t0
+
+    return fixed, tile
+
+
+def pick_threads(tile, candidates=None):
+    """torch CPU kernels stop scaling (and regress) well before all threads on these hosts: time ONE WHOLE TILE (fine
+    branch + fusion) at 32 / 64 / all threads after a warm-up tile and keep the fastest."""
+    n = os.cpu_count() or 8
+    cands = sorted(set(min(n, c) for c in (candidates or (32, 64, n))))
+    torch.set_num_threads(cands[0])
+    tile(0)                                     # warm-up (oneDNN primitive creation, allocator)
+    best, best_t, probe = cands[0], None, {}
+    for t in cands:
+        torch.set_num_threads(t)
+        dt = tile(1)
+        probe[t] = dt
+        if best_t is None or dt < best_t:
+            best, best_t = t, dt
+    return best, probe
+
+
+def cpu_baseline(encoder, cfg, sd, threads=None, reps=1, n_tiles=49):
+    """The oracle (a port of the reference algorithm) on the host cores: the per-image fixed work (coarse branch +
+    G2L) once, then `reps` micro-batches of ONE tile (fine branch + fusion); bounded sample, not the product path.
+    value = the P49-image-equivalent rate n_tiles / (t_fixed + n_tiles * t_tile)."""
+    fixed, tile = _cpu_tile_runner(encoder, cfg, sd)
+    torch.set_num_threads(min(os.cpu_count() or 8, 64))
+    t_fixed = fixed()
+    probe = None
+    if threads is None:
+        threads, probe = pick_threads(tile)
+    torch.set_num_threads(threads)
+    ts = [tile(2 + r) for r in range(reps)]
     t_tile = sum(ts) / len(ts)
-    return dict(value=1.0 / t_tile, unit='tiles/s', cores=threads, kind='port',
-                sample='%s, %d x 1 tile (fine branch + fusion, p=1) of the 4K P49 workload on %d of %d host threads '
-                       '(fastest of 8/16/32/64/all); per-image fixed work (coarse + G2L) took %.1f s and is excluded'
-                       % (encoder, reps, threads, os.cpu_count(), t_fixed),
+    value = n_tiles / (t_fixed + n_tiles * t_tile)
+    return dict(value=value, unit='tiles/s', cores=threads, kind='port',
+                sample='%s: per-image fixed work (coarse + G2L) once = %.1f s, then %d x 1 tile (fine branch + fusion, '
+                       'p=1) of the 4K P%d workload on %d of %d host threads (whole-tile probe %s); value = %d / (fixed '
+                       '+ %d x mean tile time)' % (encoder, t_fixed, reps, n_tiles, threads, os.cpu_count(),
+                                                    {k: round(v, 2) for k, v in (probe or {}).items()}, n_tiles, n_tiles),
                 s_per_tile=t_tile, s_fixed_per_image=t_fixed, tile_times=ts)
+
+
+def gpu_eager_baseline(encoder, cfg, sd, dev, n_tiles=49):
+    """The reference algorithm (oracle port) in eager PyTorch on ONE B200 with the reference's own GPU flags
+    (`estimator/utils/misc.py:24-26`: cudnn.benchmark=True; torch defaults otherwise = true-fp32 matmul, TF32 cuDNN
+    convolutions): coarse + G2L once, then the 16 tiles of the first regular pass in micro-batches of 4 (the
+    reference's default process_num).  G2L is hoisted out of the micro-batch loop (the reference recomputes it per
+    micro-batch), so this baseline is FASTER than the real reference."""
+    from oracle import pf_oracle as po
+    old = (torch.backends.cudnn.benchmark, torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.benchmark, torch.backends.cudnn.allow_tf32 = True, True
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        sdc = {k: v.to(dev) for k, v in sd.items()}
+        orc = po.Oracle(sdc, cfg)
+        img = torch.rand(1, 3, 2160, 3840, generator=torch.Generator().manual_seed(1)).to(dev)
+        P = cfg['patch_process_shape']
+        tc = po.prepare_tile_cfg((2160, 3840), (4, 4), P)
+        raws = [t[0] for t in po.tile_plan(tc, P, 'm1')[0]]
+
+        def timed(fn):
+            torch.cuda.synchronize(dev)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            r = fn()
+            e1.record()
+            torch.cuda.synchronize(dev)
+            return e0.elapsed_time(e1) / 1e3, r
+
+        with torch.no_grad():
+            lr = orc.resizer(img)
+
+            def fixed():
+                cd, cf = orc.coarse(lr)
+                return cd, cf, po.g2l_all(sdc, cf, cfg['guided_fusion'])
+
+            fixed()                                             # warm-up (cudnn.benchmark autotuning)
+            t_fixed, (cd, cf, g2l) = timed(fixed)
+            orc.tiles(img, raws[:4], cd, cf, g2l, 4, tc)        # warm-up micro-batch
+            t_tiles, _ = timed(lambda: orc.tiles(img, raws, cd, cf, g2l, 4, tc))
+        t_tile = t_tiles / len(raws)
+        return dict(value=n_tiles / (t_fixed + n_tiles * t_tile), unit='tiles/s', kind='port (oracle on cuda, eager)',
+                    flags='cudnn.benchmark=True, cudnn.allow_tf32=True (TF32 convs), matmul fp32',
+                    sample='coarse + G2L once (%.3f s) + 16 tiles (m1 pass) in micro-batches of 4 (%.3f s); value = '
+                           '%d / (fixed + %d x s_per_tile), G2L hoisted' % (t_fixed, t_tiles, n_tiles, n_tiles),
+                    s_per_tile=t_tile, s_fixed_per_image=t_fixed, p16_images_per_s=1.0 / (t_fixed + t_tiles))
+    finally:
+        torch.backends.cudnn.benchmark, torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+        torch.cuda.empty_cache()
+
+
+def dram_traffic(kernel_key):
+    """DRAM bytes per output pixel of the dominant launch shape, from the ncu --set full capture summarised under
+    profiles/ by tools/summarize_profiles.py (profiles/dram_traffic.json); None when no capture is committed."""
+    p = os.path.join(ROOT, 'profiles', 'dram_traffic.json')
+    if not os.path.exists(p):
+        return None, None
+    d = json.load(open(p)).get(kernel_key)
+    if not d:
+        return None, None
+    return d['bytes_per_unit'], d.get('source')
 
 
 def lib_summary(records):
@@ -177,14 +252,15 @@ def main():
         if rank != 0:
             return
         cfg, sd = build_inputs(enc)
-        warm = min(args.warmup, 1)          # CPU: one warm-up tile is enough; keeps the arm within minutes
-        cb = cpu_baseline(enc, cfg, sd, reps=args.steps, warm=warm)
+        warm = 2                            # CPU: the thread probe runs a warm-up tile + one tile per candidate count
+        cb = cpu_baseline(enc, cfg, sd, reps=args.steps, n_tiles=n_tiles)
         ms = cb['s_per_tile'] * 1e3
         v = cb['value']
         print(json.dumps(dict(
             impl='reference', metric='tiles/s', value=v, unit='tiles/s', n_gpus=args.gpus, steps=args.steps,
             warmup=warm, ms_per_step=ms, higher_is_better=True, scaling='weak', vs_baseline=None, dtype='f32',
-            data='synthetic', config=dict(workload=workload, note='each step = 1 tile (bounded sample) on host cores'),
+            data='synthetic', config=dict(workload=workload, note='each step = 1 tile (bounded sample) on host cores; '
+                                          'value includes the per-image fixed work amortised over the image'),
             cpu_baseline=cb, e2e=dict(value=v, unit='tiles/s', h2d_bytes_per_step=0, d2h_bytes_per_step=0),
             gpu_launches=0)))
         return
@@ -209,18 +285,22 @@ def main():
     host_img = torch.rand(1, 3, 2160, 3840, generator=g).pin_memory()
     RH, RW = model.tile_cfg['patch_reensemble_shape']
     host_out = torch.empty((1, 1, RH, RW), dtype=torch.float32).pin_memory()
-    gathered = torch.empty((world, RH, RW), dtype=torch.float32, device=dev) if world > 1 else None
 
-    def local_step(img_dev):
+    def step(img_dev):
+        # images-per-rank (weak scaling): independent images, no data-path collective
         lr = model.make_lr(img_dev)
         y, _ = model(mode='infer', image_lr=lr, image_hr=img_dev, cai_mode=args.cai_mode, process_num=args.process_num)
         return y
 
-    def step(img_dev):
-        y = local_step(img_dev)
-        if world > 1:
-            import torch.distributed as dist
-            dist.all_gather_into_tensor(gathered, y[0, 0].contiguous())
+    local_step = step
+    # tiles-per-rank (BASELINE configs[2]): ONE image (the same on every rank), tile i -> rank i % world,
+    # one all-gather of the per-rank prediction blocks, deterministic stitch on every rank
+    shared_img = torch.rand(1, 3, 2160, 3840, generator=torch.Generator().manual_seed(7)).to(dev)
+
+    def sharded_step():
+        lr = model.make_lr(shared_img)
+        y, _ = model(mode='infer', image_lr=lr, image_hr=shared_img, cai_mode=args.cai_mode,
+                     process_num=args.process_num, shard=(rank, world) if world > 1 else None)
         return y
 
     def barrier():
@@ -276,6 +356,9 @@ def main():
     ms_dev = timed(lambda: step(img_dev), args.steps)
     launches = lib.launch_count() + model.graph_launches - l0
     ms_e2e = timed(e2e_step, args.steps)
+    for _ in range(3):
+        sharded_step()
+    ms_shard = timed(sharded_step, args.steps)
     clocks = sampler.stop() if sampler else {}
 
     # roofline pass: per-launch CUDA events around every kernel of one more step (not part of the timed value)
@@ -310,11 +393,12 @@ def main():
     ms_launch = sum(r[2].elapsed_time(r[3]) for r in same) / len(same)
     ach = big[1] / (ms_launch / 1e3) / 1e12
     rows_launch = big[1] / (2.0 * 9 * 544 * 544)
-    # DRAM bytes of this launch shape from the committed ncu --set full capture (profiles/r01_halo_conv_up4_x9_full.md:
-    # 1.996 GB read + 1.947 GB written for 9 tiles = 1,827,504 output pixels), scaled to this launch's pixel count
-    traffic = (1.996231e9 + 1.946889e9) / 1827504.0 * rows_launch
+    # DRAM bytes of this launch shape: dram__bytes_read.sum + dram__bytes_write.sum of the committed ncu --set full
+    # capture, stored per output pixel in profiles/dram_traffic.json by tools/summarize_profiles.py (None if absent)
+    bpp, traffic_src = dram_traffic('pf_conv3_halo_kernel/up_conv_list.4.conv1')
+    traffic = bpp * rows_launch if bpp is not None else None
     roof = dict(bound='tensor', achieved=ach, peak=pk['tflops_sustained'], unit='TFLOP/s',
-                frac=ach / pk['tflops_sustained'], traffic=traffic,
+                frac=ach / pk['tflops_sustained'], traffic=traffic, traffic_source=traffic_src,
                 kernel='pf_conv3_halo_kernel (tcgen05 halo-tile 3x3 conv; %d launches/step, %.1f%% of step kernel '
                        'time); launch = up_conv_list.4 conv1 [32,256,256]->544 @392x518 x %d tiles, %.3f ms'
                        % (halo['launches'], 100.0 * halo['ms'] / total_ms, round(rows_launch / (392 * 518)), ms_launch),
@@ -327,9 +411,19 @@ def main():
         for k_, v in sorted(prof.items(), key=lambda kv: -kv[1]['ms']):
             sys.stderr.write('%-26s %8.2f ms %6d launches %8.1f TF/s\n' % (k_, v['ms'], v['launches'],
                                                                          v['flops'] / max(v['ms'], 1e-9) / 1e9))
-    cb = None
+    cb = ge = None
     if not args.no_cpu_baseline and world == 1:
-        cb = cpu_baseline(enc, cfg, sd, reps=1, warm=1)
+        del model
+        torch.cuda.empty_cache()
+        ge = gpu_eager_baseline(enc, cfg, sd, dev, n_tiles=n_tiles)
+        cb = cpu_baseline(enc, cfg, sd, reps=1, n_tiles=n_tiles)
+    ms_img_single = ms_dev / args.steps                  # one image on one GPU (replica mode, same run)
+    ms_img_shard = ms_shard / args.steps
+    tile_sharded = dict(ms_per_image=ms_img_shard, tiles_per_s=n_tiles / (ms_img_shard / 1e3), n_gpus=world,
+                        single_gpu_ms_per_image=ms_img_single, speedup_vs_single_gpu=ms_img_single / ms_img_shard,
+                        efficiency_vs_n1=ms_img_single / ms_img_shard / world,
+                        collective='1 all_gather_into_tensor of [ceil(%d/%d), 392, 518] fp32 blocks per image' % (n_tiles, world),
+                        tiles_on_busiest_rank=-(-n_tiles // world))
     out = dict(
         metric='tiles/s', value=tps, unit='tiles/s', n_gpus=world, steps=args.steps, warmup=max(args.warmup, 3),
         ms_per_step=ms_dev / args.steps, higher_is_better=True, scaling='weak', vs_baseline=None, dtype='bf16',
@@ -338,7 +432,8 @@ def main():
                     l2='working set >> L2: 1.5 GB bf16 weights + ~GBs of activations streamed every step'),
         e2e=dict(value=tps_e2e, unit='tiles/s', h2d_bytes_per_step=host_img.numel() * 4,
                  d2h_bytes_per_step=host_out.numel() * 4),
-        gpu_launches=launches, clocks=clocks, roofline=roof, cpu_baseline=cb)
+        gpu_launches=launches, clocks=clocks, roofline=roof, cpu_baseline=cb, gpu_eager_baseline=ge,
+        tile_sharded=tile_sharded)
     sys.stdout.flush()
     os.dup2(saved_stdout, 1)
     print(json.dumps(out), flush=True)

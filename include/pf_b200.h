@@ -161,10 +161,13 @@ int pf_swin_residual_crop(float* x, const float* y, int32_t H, int32_t W, int32_
 /* x = emb + up(prev_emb) (attractor.py:175-178), NHWC bf16 */
 int pf_add_upsampled(const void* a, int32_t B, int32_t H, int32_t W, int32_t C, const void* prev, int32_t PH,
                      int32_t PW, void* out, void* stream);
-/* b_new = up(b_prev) + mean_a inv_attractor(A_a - up(b_prev)), alpha=300, gamma=2; fp32 [B,H,W,nbins];
- * A: fp32 [B*H*W, A_ld] (first nA columns used) */
+/* b_new = up(b_prev) + agg_a dist(A_a - up(b_prev)), alpha=300, gamma=2 (the TorchScript defaults the layer always
+ * runs with, attractor.py:186-195); fp32 [B,H,W,nbins]; A: fp32 [B*H*W, A_ld] (first nA columns used).
+ * flags: PF_ATTRACTOR_MEAN (kind='mean', else 'sum') | PF_ATTRACTOR_EXP (attractor_type='exp', else 'inv'). */
+#define PF_ATTRACTOR_MEAN 1
+#define PF_ATTRACTOR_EXP 2
 int pf_attractor(const float* A, int32_t A_ld, int32_t nA, const float* b_prev, int32_t PH, int32_t PW, int32_t B, int32_t H,
-                 int32_t W, int32_t nbins, int32_t kind_mean, float* b_out, void* stream);
+                 int32_t W, int32_t nbins, int32_t flags, float* b_out, void* stream);
 /* depth = sum_k softmax_k(logbinom(p)/t) * up(b_centers)_k from the 4-channel softplus'd pt map */
 int pf_logbinom_depth(const float* pt, int32_t pt_ld, const float* b_centers, int32_t BH, int32_t BW, int32_t B, int32_t H, int32_t W,
                       int32_t nbins, float min_temp, float max_temp, float* depth, void* stream);
@@ -176,6 +179,15 @@ int pf_logbinom_depth(const float* pt, int32_t pt_ld, const float* b_centers, in
 int pf_stitch_accumulate(float* num, float* den, int32_t CH, int32_t CW, const float* tiles, int32_t T, int32_t th,
                          int32_t tw, const int32_t* origins, const float* mask, int32_t up_h, int32_t up_w,
                          void* stream);
+/* Deterministic stitch (the product path; no atomics): every canvas pixel sums, in list order, mask * prediction over
+ * the tiles covering it.  tiles: n x {origin_y, origin_x, slot} int32 (device); tile i's prediction is
+ * preds[slot_i] ([*, th, tw] fp32 - e.g. the all-gathered per-rank blocks of the tile-sharded run, so the result is
+ * bit-identical for any rank count and micro-batch grouping).  up_h/up_w > 0: nearest-upsample each tile first
+ * (random_tile).  base_num/base_den (nullable): canvases to continue from (RunningAverageMap.resize output).
+ * Outputs (each nullable): num, den, avg = num / den. */
+int pf_stitch_gather(const float* preds, const int32_t* tiles, int32_t n, int32_t th, int32_t tw, const float* mask,
+                     int32_t up_h, int32_t up_w, const float* base_num, const float* base_den, int32_t CH, int32_t CW,
+                     float* num_out, float* den_out, float* avg_out, void* stream);
 int pf_stitch_finalize(const float* num, const float* den, int64_t n, float* out, void* stream);
 /* Multi-GPU tile sharding: `stack` is the all-gathered [world][2][n] (num, den) canvases; sums over ranks in rank
  * order into stack[0] (deterministic for a fixed world size). */

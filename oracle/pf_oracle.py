@@ -178,6 +178,11 @@ def inv_attractor(dx, alpha=300.0, gamma=2):
     return dx / (1 + alpha * dx.pow(gamma))
 
 
+def exp_attractor(dx, alpha=300.0, gamma=2):
+    """ATT:29-41, same defaults."""
+    return torch.exp(-alpha * dx.abs().pow(gamma)) * dx
+
+
 def metric_head(w, x, x_blocks, last, rel_cond, hp, taps=None):
     """x: bottleneck (B,C,h0,w0); x_blocks: 4 maps low->high; last: (B,32,H,W); rel_cond: (B,1,H,W)."""
     b_prev = _mlp2(w.sub('seed_bin_regressor.'), x, F.softplus)
@@ -187,8 +192,9 @@ def metric_head(w, x, x_blocks, last, rel_cond, hp, taps=None):
         size = xb.shape[-2:]
         A = _mlp2(w.sub('attractors.%d.' % i), emb + up(prev_emb, size), F.softplus)
         b = up(b_prev, size)
-        delta = inv_attractor(A.unsqueeze(2) - b.unsqueeze(1))
-        kind = _get(hp, 'attractor_kind', 'mean')
+        dist = exp_attractor if _get(hp, 'attractor_type', 'exp') == 'exp' else inv_attractor       # ATT:186-189
+        delta = dist(A.unsqueeze(2) - b.unsqueeze(1))
+        kind = _get(hp, 'attractor_kind', 'sum')
         delta = delta.mean(dim=1) if kind == 'mean' else delta.sum(dim=1)
         b_prev, prev_emb = b + delta, emb
         if taps is not None:

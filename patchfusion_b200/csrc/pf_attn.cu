@@ -461,7 +461,8 @@ using namespace pf;
 
 extern "C" int pf_attention(const void* qk, int32_t qk_ld, const void* vt, int32_t B, int32_t seq, int32_t seq_pad,
                             int32_t heads, float scale, void* out, int32_t out_ld, void* stream) {
-  static bool attr_done = false;
+  static bool attr_done_dev[kMaxDevices] = {false};
+  bool& attr_done = attr_done_dev[current_device()];
   static const bool use_v1 = getenv("PF_B200_ATTN_V1") != nullptr;
   const int smem_bytes = 1024 + 81920 + 128 + 3072;
   if (!attr_done) {

@@ -550,10 +550,10 @@ __global__ void add_upsampled_kernel(const bf16* __restrict__ a, int B, int H, i
   *reinterpret_cast<uint4*>(out + p * C + g * 8) = pack8(o);
 }
 
-// one warp per pixel (grid-stride), 2 bins per lane (nbins == 64): b = up(b_prev); b += mean_a( dx / (1 + 300 dx^2) ),
-// dx = A_a - b.  The <= 16 attractor points of the pixel are read once per warp.
+// one warp per pixel (grid-stride), 2 bins per lane (nbins == 64): b = up(b_prev); b += mean_a|sum_a( dist(dx) ),
+// dx = A_a - b, dist = inverse (dx / (1 + 300 dx^2)) or exponential (exp(-300 dx^2) dx) attractor.  The <= 16 attractor points of the pixel are read once per warp.
 __global__ void attractor_kernel(const float* __restrict__ A, int A_ld, int nA, const float* __restrict__ b_prev, int PH,
-                                 int PW, int B, int H, int W, int nbins, int kind_mean, float sy, float sx,
+                                 int PW, int B, int H, int W, int nbins, int kind_mean, int type_exp, float sy, float sx,
                                  float* __restrict__ b_out) {
   const int lane = threadIdx.x & 31;
   const int warps = (gridDim.x * blockDim.x) >> 5;
@@ -582,7 +582,9 @@ __global__ void attractor_kernel(const float* __restrict__ A, int A_ld, int nA, 
 #pragma unroll
       for (int i = 0; i < 2; ++i) {
         const float dx = aa - bc[i];
-        s[i] += dx / (1.f + 300.f * dx * dx);
+        // attractor.py:44-57 / 29-41 with the TorchScript defaults alpha=300, gamma=2 (the layer never forwards the
+        // configured values, attractor.py:191-195)
+        s[i] += type_exp ? __expf(-300.f * dx * dx) * dx : dx / (1.f + 300.f * dx * dx);
       }
     }
 #pragma unroll
@@ -694,6 +696,42 @@ __global__ void stitch_accumulate_kernel(float* __restrict__ num, float* __restr
     atomicAdd(num + o, m * d);
     atomicAdd(den + o, m);
   }
+}
+
+// Deterministic stitch: each canvas pixel sums, in tile-list order, the (mask-weighted) predictions of the tiles
+// that cover it - no atomics, so the canvas is bit-identical for any micro-batch grouping and any rank count (the
+// list order is the single-device order; `slot` says where tile i's prediction sits in the gathered blocks).
+// tiles: n x {origin y, origin x, slot}.  base_*: canvases of a previous phase to continue from (nullable).
+__global__ void stitch_gather_kernel(const float* __restrict__ preds, const int* __restrict__ tiles, int n, int th, int tw,
+                                     const float* __restrict__ mask, int uh, int uw, const float* __restrict__ base_num,
+                                     const float* __restrict__ base_den, int CH, int CW, float* __restrict__ num_out,
+                                     float* __restrict__ den_out, float* __restrict__ avg_out) {
+  extern __shared__ int s_tiles[];
+  for (int i = threadIdx.y * blockDim.x + threadIdx.x; i < 3 * n; i += blockDim.x * blockDim.y) s_tiles[i] = tiles[i];
+  __syncthreads();
+  const int cx = blockIdx.x * blockDim.x + threadIdx.x, cy = blockIdx.y * blockDim.y + threadIdx.y;
+  if (cx >= CW || cy >= CH) return;
+  const int oh = uh > 0 ? uh : th, ow = uw > 0 ? uw : tw;
+  const float ry = static_cast<float>(th) / oh, rx = static_cast<float>(tw) / ow;
+  const long long o = static_cast<long long>(cy) * CW + cx;
+  float num = base_num ? base_num[o] : 0.f, den = base_den ? base_den[o] : 0.f;
+  for (int i = 0; i < n; ++i) {
+    const int y = cy - s_tiles[3 * i], x = cx - s_tiles[3 * i + 1];
+    if (static_cast<unsigned>(y) < static_cast<unsigned>(oh) && static_cast<unsigned>(x) < static_cast<unsigned>(ow)) {
+      int sy = y, sx = x;
+      if (uh > 0) {   // F.interpolate default 'nearest' (baseline_pretrain.py:203): src = floor(dst * in/out)
+        sy = min(static_cast<int>(floorf(y * ry)), th - 1);
+        sx = min(static_cast<int>(floorf(x * rx)), tw - 1);
+      }
+      const float d = preds[(static_cast<long long>(s_tiles[3 * i + 2]) * th + sy) * tw + sx];
+      const float m = mask[static_cast<long long>(y) * ow + x];
+      num += m * d;
+      den += m;
+    }
+  }
+  if (num_out) num_out[o] = num;
+  if (den_out) den_out[o] = den;
+  if (avg_out) avg_out[o] = num / den;
 }
 
 __global__ void stitch_finalize_kernel(const float* __restrict__ num, const float* __restrict__ den, long long n,
@@ -897,12 +935,14 @@ int pf_add_upsampled(const void* a, int32_t B, int32_t H, int32_t W, int32_t C, 
 }
 
 int pf_attractor(const float* A, int32_t A_ld, int32_t nA, const float* b_prev, int32_t PH, int32_t PW, int32_t B,
-                 int32_t H, int32_t W, int32_t nbins, int32_t kind_mean, float* b_out, void* stream) {
+                 int32_t H, int32_t W, int32_t nbins, int32_t flags, float* b_out, void* stream) {
   if (nbins != 64 || nA > 32) return set_error("pf_attractor: n_bins must be 64 and n_attractors <= 32");
+  if (flags & ~3) return set_error("pf_attractor: unknown flags %d", flags);
+  const int kind_mean = flags & PF_ATTRACTOR_MEAN, type_exp = (flags & PF_ATTRACTOR_EXP) ? 1 : 0;
   long long warps_needed = static_cast<long long>(B) * H * W;
   unsigned blocks = static_cast<unsigned>(warps_needed < 148 * 8 * 8 ? (warps_needed + 7) / 8 : 148 * 8);
-  attractor_kernel<<<blocks, 256, 0, ST>>>(A, A_ld, nA, b_prev, PH, PW, B, H, W, nbins, kind_mean, ac_scale(PH, H),
-                                           ac_scale(PW, W), b_out);
+  attractor_kernel<<<blocks, 256, 0, ST>>>(A, A_ld, nA, b_prev, PH, PW, B, H, W, nbins, kind_mean, type_exp,
+                                           ac_scale(PH, H), ac_scale(PW, W), b_out);
   return check_launch("attractor_kernel");
 }
 
@@ -922,6 +962,17 @@ int pf_stitch_accumulate(float* num, float* den, int32_t CH, int32_t CW, const f
   stitch_accumulate_kernel<<<nblocks(total, 256), 256, 0, ST>>>(num, den, CH, CW, tiles, T, th, tw, origins, mask, up_h,
                                                                  up_w);
   return check_launch("stitch_accumulate_kernel");
+}
+
+int pf_stitch_gather(const float* preds, const int32_t* tiles, int32_t n, int32_t th, int32_t tw, const float* mask,
+                     int32_t up_h, int32_t up_w, const float* base_num, const float* base_den, int32_t CH, int32_t CW,
+                     float* num_out, float* den_out, float* avg_out, void* stream) {
+  if (n < 0 || n > 4096) return set_error("pf_stitch_gather: n %d out of range (0..4096)", n);
+  if ((up_h > 0) != (up_w > 0)) return set_error("pf_stitch_gather: up_h/up_w must both be set or both be 0");
+  dim3 block(32, 8), grid((CW + 31) / 32, (CH + 7) / 8);
+  stitch_gather_kernel<<<grid, block, static_cast<size_t>(n) * 12, ST>>>(preds, tiles, n, th, tw, mask, up_h, up_w, base_num,
+                                                                       base_den, CH, CW, num_out, den_out, avg_out);
+  return check_launch("stitch_gather_kernel");
 }
 
 int pf_stitch_finalize(const float* num, const float* den, int64_t n, float* out, void* stream) {

@@ -567,19 +567,21 @@ __global__ void __launch_bounds__(kGemmThreads, 1) pf_conv3_halo_kernel(const __
 // ------------------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------------------
-static int g_sm_count = 0;
+static int g_sm_counts[kMaxDevices] = {0};
 
 int gemm_launch(const GemmDesc& d, const CUtensorMap* tmA, const CUtensorMap& tmB, cudaStream_t stream) {
-  static bool attr_done = false;
+  static bool attr_done[kMaxDevices] = {false};
   const int kMaxSmem = 227 * 1024;
-  if (!attr_done) {
+  const int dev = current_device();
+  if (!attr_done[dev]) {
     cudaError_t e = cudaFuncSetAttribute(pf_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
     if (e != cudaSuccess) return set_error("cudaFuncSetAttribute(pf_gemm_kernel): %s", cudaGetErrorString(e));
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev);
-    attr_done = true;
+    e = cudaFuncSetAttribute(pf_conv3_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
+    if (e != cudaSuccess) return set_error("cudaFuncSetAttribute(pf_conv3_halo_kernel): %s", cudaGetErrorString(e));
+    cudaDeviceGetAttribute(&g_sm_counts[dev], cudaDevAttrMultiProcessorCount, dev);
+    attr_done[dev] = true;
   }
+  const int g_sm_count = g_sm_counts[dev];
   if (d.block_n % 32 != 0 || d.block_n < 32 || d.block_n > 256) return set_error("gemm: bad block_n %d", d.block_n);
   GemmKernelParams P;
   for (int s = 0; s < d.num_src; ++s) P.tmA[s] = tmA[s];
@@ -601,12 +603,6 @@ int gemm_launch(const GemmDesc& d, const CUtensorMap* tmA, const CUtensorMap& tm
   int grid = P.total_tiles < g_sm_count ? P.total_tiles : g_sm_count;
   size_t smem = 1024 + static_cast<size_t>(stages) * stage_bytes + kTailBytes;
   if (d.halo) {
-    static bool halo_attr = false;
-    if (!halo_attr) {
-      cudaError_t e2 = cudaFuncSetAttribute(pf_conv3_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
-      if (e2 != cudaSuccess) return set_error("cudaFuncSetAttribute(pf_conv3_halo_kernel): %s", cudaGetErrorString(e2));
-      halo_attr = true;
-    }
     int b_bytes = d.block_n * kBlockK * 2;
     int hb = kMaxSmem - 1024 - kTailBytes - kHaloSlots * kHaloSlot;
     // taps per weight stage: amortise the per-stage barrier round trip (~500 clk) over >= ~512 clk of MMA work

@@ -37,6 +37,14 @@ struct GemmDesc {
 };
 
 int set_error(const char* fmt, ...);
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) and the SM count are per DEVICE: one-time setup is keyed by the
+// current device so one process can drive engines on several GPUs.
+constexpr int kMaxDevices = 64;
+inline int current_device() {
+  int d = 0;
+  cudaGetDevice(&d);
+  return (d < 0 || d >= kMaxDevices) ? 0 : d;
+}
 bool pdl_enabled();
 
 // <<<>>> replacement that sets the programmatic-stream-serialization attribute (kernels launched through it call

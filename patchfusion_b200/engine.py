@@ -352,7 +352,7 @@ class Engine:
         depth = self.metric_head(which + slot + '.head.', Wd['head'], hp, self.bcfg[which], x_d0, blocks, out_conv, rel, taps)
         return depth, [x_d0] + blocks + [out_conv]
 
-    def metric_head(self, k, Wh, hp, bcfg, x, x_blocks, last, rel, taps=None):
+    def metric_head(self, k, Wh, hp, bcfg, x, x_blocks, last, rel, taps=None, depth_out=None):
         """zoedepth_v1.py:173-219 / patchfusion.py:297-339.  rel: Map fp32 [B,H,W,8] (col 0) or None."""
         st = stream_ptr()
         B = x.B
@@ -386,7 +386,7 @@ class Engine:
             A = mlp('att%d' % i, 'attractors.%d' % i, s, ACT_SOFTPLUS, f32_out=True)
             b_new = self.buf(k + 'b%d' % i, (B, h, w, nb), F32)
             call('pf_attractor', A.t, A.t.shape[-1], hp['n_attractors'][i], b_t, ph, pw_, B, h, w, nb,
-                 1 if _get(bcfg, 'attractor_kind', 'mean') == 'mean' else 0, b_new, st)
+                 (1 if hp['attractor_kind'] == 'mean' else 0) | (2 if hp['attractor_type'] == 'exp' else 0), b_new, st)
             b_t, ph, pw_, prev_emb = b_new, h, w, emb
             if taps is not None:
                 taps['b%d' % i] = b_new.clone()
@@ -402,7 +402,8 @@ class Engine:
         # CLB MLP: 1x1 (161->80) + GELU with the 80->4 + Softplus layer fused in its epilogue (dist_layers.py:91-98)
         self.conv(k + 'clb0', Wh['clb.0'], srcs, act=ACT_GELU, tail=Wh['clb.tail'] + (ACT_SOFTPLUS,), tail_out=pt,
                   skip_main=True)
-        depth = self.buf(k + 'depth', (B, H, Wimg), F32)
+        depth = self.buf(k + 'depth', (B, H, Wimg), F32) if depth_out is None else depth_out
+        assert depth.dtype == F32 and depth.is_contiguous() and tuple(depth.shape) == (B, H, Wimg)
         call('pf_logbinom_depth', pt, 8, b_t, ph, pw_, B, H, Wimg, nb, ct.c_float(_get(bcfg, 'min_temp')),
              ct.c_float(_get(bcfg, 'max_temp')), depth, st)
         return depth
@@ -420,6 +421,10 @@ class Engine:
             Hp, Wp = math.ceil(h / WINDOW) * WINDOW, math.ceil(w / WINDOW) * WINDOW
             k = 'g2l%d.' % i
             x = self.buf(k + 'x', (n, c), F32)
+            # the reference adds absolute_pos_embed (1, num_patches, C) to the (1, h*w, C) tokens (swin_layers.py:421-422)
+            # and would fail on the broadcast if they differ
+            assert L['ape'].shape[0] == n, 'guided_fusion.num_patches[%d] = %d does not match the %dx%d coarse map' % (
+                i, L['ape'].shape[0], h, w)
             call('pf_g2l_embed', f.t, f.t.shape[-1], L['ape'], n, c, x, st)
             npad = self.buf(k + 'npad', (Hp * Wp, c))
             qkv = self.buf(k + 'qkv', (Hp * Wp, 3 * c))
@@ -443,7 +448,8 @@ class Engine:
         return outs
 
     # ------------------------------------------------------------------ fusion of T tiles
-    def fusion(self, crops, boxes, fine_depth, fine_feats, coarse_depth, coarse_feats, g2l_maps, taps=None):
+    def fusion(self, crops, boxes, fine_depth, fine_feats, coarse_depth, coarse_feats, g2l_maps, taps=None,
+               depth_out=None):
         """crops planar fp32 [T,3,H,W]; boxes fp32 [T,4] (device, patch_process units); returns fp32 [T,H,W]."""
         Wf = self.W['fusion']
         st = stream_ptr()
@@ -492,4 +498,4 @@ class Engine:
             if taps is not None:
                 taps['fuse%d' % i] = prev.t.clone()
         return self.metric_head('fus.head.', Wf['head'], self.hp['coarse'], self.bcfg['coarse'], outs[0], outs[1:5],
-                                outs[5], None, taps)
+                                outs[5], None, taps, depth_out=depth_out)

@@ -68,6 +68,7 @@ SIGNATURES = {
     'pf_attractor': [_p, _i, _i, _p, _i, _i, _i, _i, _i, _i, _i, _p, _p],
     'pf_logbinom_depth': [_p, _i, _p, _i, _i, _i, _i, _i, _i, _f, _f, _p, _p],
     'pf_stitch_accumulate': [_p, _p, _i, _i, _p, _i, _i, _i, _p, _p, _i, _i, _p],
+    'pf_stitch_gather': [_p, _p, _i, _i, _i, _p, _i, _i, _p, _p, _i, _i, _p, _p, _p, _p],
     'pf_stitch_finalize': [_p, _p, _ll, _p, _p],
     'pf_stitch_reduce': [_p, _i, _ll, _p],
     'pf_stitch_resize': [_p, _p, _i, _i, _i, _i, _p, _p, _p],

@@ -115,10 +115,15 @@ class PatchFusion(ParamTree, PyTorchModelHubMixin):
         self._coarse = None
         self.use_cuda_graphs = os.environ.get('PF_B200_GRAPHS', '1') != '0'
         self.partition = os.environ.get('PF_B200_PARTITION', 'greedy')
-        self.overlap = os.environ.get('PF_B200_OVERLAP', '0') != '0'    # opt-in: +1 % on one GPU, see DESIGN.md
+        # coarse branch + G2L (batch 1) on a side stream next to the first fine branch: measured in DESIGN.md
+        self.overlap_coarse = os.environ.get('PF_B200_OVERLAP_COARSE', '1') != '0'
         self._side_stream = None
-        self._fine_out = {}
         self._mask_cache = {}
+        # sub-module loads (model.fine_branch.load_state_dict(sd), as the load_branch constructor path does) and
+        # .to()/.half() on a sub-module must drop the packed bf16 panels too: hook every container node
+        for m in self.modules():
+            if m is not self:
+                m.register_load_state_dict_post_hook(lambda mod, inc, _s=self: _s.invalidate())
         if config.load_branch:
             for which, path in zip(('coarse_branch', 'fine_branch'), config.pretrain_model):
                 sd = torch.load(path, map_location='cpu')['model_state_dict']
@@ -156,11 +161,11 @@ class PatchFusion(ParamTree, PyTorchModelHubMixin):
         return {k: v for k, v in self.state_dict().items() if 'coarse_branch' not in k and 'fine_branch' not in k}
 
     def load_state_dict(self, *a, **kw):
-        self._engine, self._graphs = None, {}
+        self.invalidate()
         return super().load_state_dict(*a, **kw)
 
     def _apply(self, fn, *a, **kw):
-        self._engine, self._graphs = None, {}
+        self.invalidate()
         return super()._apply(fn, *a, **kw)
 
     def init_synthetic_weights(self, seed=0):
@@ -261,7 +266,7 @@ class PatchFusion(ParamTree, PyTorchModelHubMixin):
     def _graphed(self, key, fn):
         """Run `fn` (a fixed kernel sequence over static buffers) through a CUDA graph: first call runs eagerly
         (allocating the engine buffers and caching the TMA maps) and captures, later calls replay.  One graph per
-        (stage, micro-batch size, geometry): ~900 launches per micro-batch collapse into one host call."""
+        (phase, micro-batch sizes, geometry): the ~2800 launches of a 4K P49 image collapse into one host call."""
         from . import lib
         if not self.use_cuda_graphs or lib.PROFILER is not None:
             return fn()
@@ -279,185 +284,192 @@ class PatchFusion(ParamTree, PyTorchModelHubMixin):
         self.graph_launches += ent[1]          # kernels executed by the replay (for bench.py's gpu_launches)
         return None
 
+    def invalidate(self):
+        """Drop the packed-weight engine and the captured graphs (call after editing parameters in place; state-dict
+        loads and `.to()` on the model or any sub-module do it automatically)."""
+        self._engine, self._graphs = None, {}
+
     def _coarse_stage(self, eng, lr):
         cd, cf = eng.branch('coarse', lr)
         self._coarse = (cd[0], cf, eng.g2l(cf))
 
-    def _fine_stage(self, eng, img, T, geom, par=0):
-        """crop+resize -> fine branch for the T tiles whose origins sit in the static buffers of `_tile_io(T, par)`."""
+    def _fine_stage(self, eng, img, T, geom, raw):
+        """crop+resize -> fine branch for the T tiles whose raw origins are the device rows `raw` ([T,2] int32)."""
         from . import ops
         H, W, h, w, ph, pw = geom
-        io = self._tile_io(eng, T, par)
-        crops = eng.buf('tile.crops%d' % par, (T, 3, ph, pw), torch.float32)
-        ops.call('pf_crop_resize', img, H, W, io['raw'], T, h, w, ph, pw, crops, ops.stream_ptr())
-        fd, ff = eng.branch('fine', crops, slot=str(par) if par else '')
-        self._fine_out[par] = (crops, fd, ff)
+        crops = eng.buf('tile.crops', (T, 3, ph, pw), torch.float32)
+        ops.call('pf_crop_resize', img, H, W, raw, T, h, w, ph, pw, crops, ops.stream_ptr())
+        fd, ff = eng.branch('fine', crops)
+        return crops, fd, ff
 
-    def _fusion_stage(self, eng, T, geom, canvas, mask, up, par=0):
-        """guided fusion + scatter-stitch of the micro-batch whose fine-branch outputs sit in slot `par`."""
-        from . import ops
-        H, W, h, w, ph, pw = geom
-        num, den, CH, CW = canvas
-        io = self._tile_io(eng, T, par)
+    def _fusion_stage(self, eng, fine, boxes, out):
+        """guided fusion of one micro-batch; the fused depth goes straight into its rows `out` of the prediction block."""
         cd, cf, g2l = self._coarse
-        crops, fd, ff = self._fine_out[par]
-        pred = eng.fusion(crops, io['boxes'], fd, ff, cd, cf, g2l)
-        ops.call('pf_stitch_accumulate', num, den, CH, CW, pred, T, ph, pw, io['dst'], mask, up[0], up[1],
-                 ops.stream_ptr())
+        crops, fd, ff = fine
+        eng.fusion(crops, boxes, fd, ff, cd, cf, g2l, depth_out=out)
 
-    def _tiles_stage(self, eng, img, T, geom, canvas, mask, up):
-        self._fine_stage(eng, img, T, geom, 0)
-        self._fusion_stage(eng, T, geom, canvas, mask, up, 0)
-
-    def _pair_stage(self, eng, img, geom, canvas, mask, up, fus, fine):
-        """fusion of micro-batch k (slot fus[1]) on the current stream while the fine branch of micro-batch k+1
-        (slot fine[1]) runs on a side stream: the two have no data dependency, so their kernels fill each other's
-        partial waves and launch gaps."""
-        cur = torch.cuda.current_stream()
-        if self._side_stream is None:
-            self._side_stream = torch.cuda.Stream()
-        side = self._side_stream
-        side.wait_stream(cur)
-        with torch.cuda.stream(side):
-            self._fine_stage(eng, img, fine[0], geom, fine[1])
-        self._fusion_stage(eng, fus[0], geom, canvas, mask, up, fus[1])
-        cur.wait_stream(side)
-
-    def _combine_canvases(self, num, den, base=None):
-        """ONE all-gather of the stacked (num, den) canvases + fixed-order sum (pf_stitch_reduce)."""
-        from . import ops
-        from .parallel import gather_canvases
-        stack = gather_canvases(num, den)
-        ops.call('pf_stitch_reduce', stack, stack.shape[0], ops.C.c_int64(num.numel()), ops.stream_ptr())
-        n, d = stack[0, 0], stack[0, 1]
-        if base is not None:
-            n, d = n + base[0], d + base[1]
-        return n.contiguous(), d.contiguous()
-
-    def _tile_io(self, eng, T, par=0):
-        return dict(raw=eng.buf('tile.raw%d' % par, (T, 2), torch.int32),
-                    dst=eng.buf('tile.dst%d' % par, (T, 2), torch.int32),
-                    boxes=eng.buf('tile.boxes%d' % par, (T, 4), torch.float32))
-
-    def _run_tiles(self, eng, img, raw, dst, geom, canvas, mask, up, process_num):
-        H, W, h, w, ph, pw = geom
-        fx = np.float32(1 / W * pw)
-        fy = np.float32(1 / H * ph)
-        # balanced micro-batches (e.g. 49 tiles, process_num 9 -> 9,8,8,8,8,8): at most two captured graph sizes
-        # and no ragged tail; grouping does not change any tile's result
-        nchunk = -(-len(raw) // process_num)
-        if self.partition == 'balanced':
-            sizes = [len(raw) // nchunk + (1 if i < len(raw) % nchunk else 0) for i in range(nchunk)]
-        else:                                   # 'greedy': full micro-batches + one remainder (the reference's split)
-            sizes = [min(process_num, len(raw) - i * process_num) for i in range(nchunk)]
-        def load_io(i, s0, par):
-            T = sizes[i]
-            chunk = raw[s0:s0 + T]
-            io = self._tile_io(eng, T, par)
-            io['raw'].copy_(torch.tensor(chunk, dtype=torch.int32))
-            io['dst'].copy_(torch.tensor(dst[s0:s0 + T], dtype=torch.int32))
-            # boxes exactly as baseline_pretrain.py:268-282: int pixel box * fp32 factor
-            bx = np.array([[np.float32(x) * fx, np.float32(y) * fy, np.float32(x + w) * fx, np.float32(y + h) * fy]
-                           for (y, x) in chunk], dtype=np.float32)
-            io['boxes'].copy_(torch.from_numpy(bx))
-
-        gkey = tuple(geom) + (canvas[2], canvas[3]) + tuple(up)
-        starts = [sum(sizes[:i]) for i in range(len(sizes))]
+    def _image_stage(self, eng, lr, img, geom, sizes, io_raw, io_box, blk, with_coarse):
+        """The static kernel sequence of one phase of one image on this rank: [coarse branch + G2L] and the
+        micro-batches (fine branch + fusion each).  The coarse stage has no dependency on the first fine branch, so it
+        runs on a side stream next to it (its batch-1 kernels fill a fraction of the SMs)."""
         from . import lib
-        if not (self.overlap and self.use_cuda_graphs and lib.PROFILER is None and len(sizes) > 1):
-            for i, T in enumerate(sizes):
-                load_io(i, starts[i], 0)
-                self._graphed(('tiles', T) + gkey, lambda: self._tiles_stage(eng, img, T, geom, canvas, mask, up))
-            return
-        # software pipeline over micro-batches: fine(0) | fusion(k) || fine(k+1) | fusion(last)
-        load_io(0, starts[0], 0)
-        self._graphed(('fine', sizes[0], 0) + gkey, lambda: self._fine_stage(eng, img, sizes[0], geom, 0))
-        for i in range(len(sizes) - 1):
-            pf_, pn_ = i & 1, (i + 1) & 1
-            load_io(i + 1, starts[i + 1], pn_)
-            self._graphed(('pair', sizes[i], pf_, sizes[i + 1], pn_) + gkey,
-                          lambda: self._pair_stage(eng, img, geom, canvas, mask, up, (sizes[i], pf_), (sizes[i + 1], pn_)))
-        last = len(sizes) - 1
-        self._graphed(('fusion', sizes[last], last & 1) + gkey,
-                      lambda: self._fusion_stage(eng, sizes[last], geom, canvas, mask, up, last & 1))
+        cur = torch.cuda.current_stream()
+        side = None
+        if with_coarse:
+            if self.overlap_coarse and lib.PROFILER is None and sizes:
+                if self._side_stream is None:
+                    self._side_stream = torch.cuda.Stream()
+                side = self._side_stream
+                side.wait_stream(cur)
+                with torch.cuda.stream(side):
+                    self._coarse_stage(eng, lr)
+            else:
+                self._coarse_stage(eng, lr)
+        s0 = 0
+        for T in sizes:
+            fine = self._fine_stage(eng, img, T, geom, io_raw[s0:s0 + T])
+            if side is not None:
+                cur.wait_stream(side)
+                side = None
+            self._fusion_stage(eng, fine, io_box[s0:s0 + T], blk[s0:s0 + T])
+            s0 += T
+
+    def _micro_sizes(self, n, process_num):
+        nchunk = -(-n // process_num)
+        if self.partition == 'balanced':        # e.g. 49 tiles, process_num 9 -> 9,8,8,8,8,8
+            return [n // nchunk + (1 if i < n % nchunk else 0) for i in range(nchunk)]
+        return [min(process_num, n - i * process_num) for i in range(nchunk)]     # the reference's split (BP:293)
+
+    def _compute_phase(self, eng, phase, lr, img, geom, raw, process_num, shard):
+        """Fused predictions of this rank's tiles of the (global, ordered) tile list `raw` -> its block
+        [ceil(n / world), ph, pw] fp32 (row j = global tile rank + j * world)."""
+        from .parallel import shard_indices
+        H, W, h, w, ph, pw = geom
+        rank, world = (0, 1) if shard is None else shard
+        n = len(raw)
+        own = shard_indices(n, rank, world)
+        blk = eng.buf('pred.blk.' + phase, (max(-(-n // world), 1), ph, pw), torch.float32)
+        if not own:
+            return blk
+        io_raw = eng.buf('io.raw.' + phase, (len(own), 2), torch.int32)
+        io_box = eng.buf('io.box.' + phase, (len(own), 4), torch.float32)
+        fx, fy = np.float32(1 / W * pw), np.float32(1 / H * ph)
+        chunk = [raw[i] for i in own]
+        io_raw.copy_(torch.tensor(chunk, dtype=torch.int32))
+        # boxes exactly as baseline_pretrain.py:268-282: int pixel box * fp32 factor
+        io_box.copy_(torch.from_numpy(np.array(
+            [[np.float32(x) * fx, np.float32(y) * fy, np.float32(x + w) * fx, np.float32(y + h) * fy]
+             for (y, x) in chunk], dtype=np.float32)))
+        sizes = self._micro_sizes(len(own), process_num)
+        with_coarse = phase == 'reg'
+        key = ('image', phase, tuple(sizes), blk.shape[0]) + tuple(geom)
+        self._graphed(key, lambda: self._image_stage(eng, lr, img, geom, sizes, io_raw, io_box, blk, with_coarse))
+        return blk
+
+    def _exchange(self, compute, shard, group):
+        """The ONE collective of the tile-sharded path: all-gather of the per-rank prediction blocks.
+        shard=None: single device.  shard=('emulate', W): the W ranks are computed one after the other in this
+        process (test hook for 1-GPU boxes; same blocks, same stitch)."""
+        if shard is None:
+            return compute(None)
+        if shard[0] == 'emulate':
+            return torch.cat([compute((r, shard[1])).clone() for r in range(shard[1])])
+        from .parallel import gather_blocks
+        return gather_blocks(compute(shard), shard[1], group)
+
+    def _stitch_phase(self, eng, phase, full, origins, world, th, tw, mask, up, base, canvas, want):
+        """pf_stitch_gather over the global tile list (deterministic order) -> requested canvases."""
+        from . import ops
+        from .parallel import slot_table
+        CH, CW = canvas
+        n = len(origins)
+        slots = slot_table(n, world)
+        tab = eng.buf('stitch.tab.' + phase, (n, 3), torch.int32)
+        tab.copy_(torch.tensor([(oy, ox, sl) for (oy, ox), sl in zip(origins, slots)], dtype=torch.int32))
+        dev = full.device
+        outs = {k: torch.empty((CH, CW), dtype=torch.float32, device=dev) for k in want}
+        ops.call('pf_stitch_gather', full, tab, n, th, tw, mask, up[0], up[1],
+                 base[0] if base else None, base[1] if base else None, CH, CW,
+                 outs.get('num'), outs.get('den'), outs.get('avg'), ops.stream_ptr())
+        return outs
+
+    def _draw_random_boxes(self, n_calls, process_num, H, W, h, w, shard, group, dev):
+        """Random tile origins in the reference's draw order (baseline_pretrain.py:155-156: process_num rows, then ONE
+        shared column per call).  Under real sharding rank 0's draws are broadcast so every rank stitches the same
+        list (all ranks still advance their own `random` state identically)."""
+        boxes = []
+        for _ in range(n_calls):
+            ys = [random.randint(0, H - h - 1) for _ in range(process_num)]
+            x0 = random.randint(0, W - w - 1)
+            boxes += [(y, x0) for y in ys]
+        if shard is not None and shard[0] != 'emulate' and boxes:
+            import torch.distributed as dist
+            t = torch.tensor(boxes, dtype=torch.int32, device=dev if dist.get_backend(group) == 'nccl' else 'cpu')
+            dist.broadcast(t, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+            boxes = [tuple(b) for b in t.cpu().tolist()]
+        return boxes
 
     @torch.no_grad()
     def forward(self, mode, image_lr, image_hr, depth_gt=None, crops_image_hr=None, crop_depths=None, bboxs=None,
-                tile_cfg=None, cai_mode='m1', process_num=4, shard=None):
-        """`shard=(rank, world)` (extension): process only this rank's tiles and combine the canvases with one
-        all-gather (patchfusion_b200/parallel.py); None reproduces the reference's single-device behaviour."""
+                tile_cfg=None, cai_mode='m1', process_num=4, shard=None, group=None):
+        """`shard=(rank, world)` (extension): this rank runs tiles rank, rank+world, ... of the flattened tile list and
+        ONE all-gather of the per-rank prediction blocks (patchfusion_b200/parallel.py) precedes the deterministic
+        stitch, so the canvas is bit-identical to the single-device one.  `group`: the process group of `world` ranks
+        (default group if None).  shard=None reproduces the reference's single-device behaviour."""
         if mode == 'train':
             raise NotImplementedError('training is out of scope of the B200 hot-path build (SURVEY.md §2 rows 10,12)')
-        from . import ops
         if tile_cfg is None:
             tile_cfg = self.tile_cfg
         else:
             tile_cfg = self.prepare_tile_cfg(tile_cfg['image_raw_shape'], tile_cfg['patch_split_num'])
         assert image_hr.shape[0] == 1
+        if shard is not None and shard[0] != 'emulate':
+            import torch.distributed as dist
+            assert dist.is_initialized() and dist.get_world_size(group) == shard[1] and dist.get_rank(group) == shard[0], \
+                'shard=(rank, world) must match the process group the blocks are gathered over'
         eng = self.engine()
         dev = image_hr.device
-        st = ops.stream_ptr
         H, W = tile_cfg['image_raw_shape']
         assert tuple(image_hr.shape[-2:]) == (H, W), 'image_hr must already be at image_raw_shape'
         h, w = tile_cfg['patch_raw_shape']
         ph, pw = self.patch_process_shape
         RH, RW = tile_cfg['patch_reensemble_shape']
         geom = (H, W, h, w, ph, pw)
+        world = 1 if shard is None else shard[1]
         # inputs into static buffers (stable addresses for the captured graphs)
         img = eng.buf('in.image_hr', (3, H, W), torch.float32)
         img.copy_(image_hr[0])
         lr = eng.buf('in.image_lr', (1, 3, ph, pw), torch.float32)
         lr.copy_(image_lr)
-
-        self._graphed(('coarse', ph, pw), lambda: self._coarse_stage(eng, lr))
-
-        num = eng.buf('canvas.num', (RH, RW), torch.float32)
-        den = eng.buf('canvas.den', (RH, RW), torch.float32)
-        num.zero_()
-        den.zero_()
         mask = self._mask((ph, pw), dev)
         offsets = [((0, 0), (0, 0))]
         if cai_mode == 'm2' or cai_mode[0] == 'r':
             offsets += [((0, w // 2), (0, pw // 2)), ((h // 2, 0), (ph // 2, 0)), ((h // 2, w // 2), (ph // 2, pw // 2))]
         # The regular passes (baseline_pretrain.py:221-331, patchfusion.py:417-439) are independent tiles whose
-        # stitch is a commutative weighted sum, so all passes are flattened into one tile list and micro-batched.
+        # stitch is a weighted sum, so all passes are flattened into one ordered tile list and micro-batched.
         raw, proc = [], []
         for (oy, ox), (py, px) in offsets:
             assert ox >= 0 and oy >= 0
             ny, nx = (H - oy) // h, (W - ox) // w
             raw += [(h * a + oy, w * b + ox) for a in range(ny) for b in range(nx)]
             proc += [(ph * a + py, pw * b + px) for a in range(ny) for b in range(nx)]
-        if shard is not None:
-            from .parallel import shard_indices
-            own = shard_indices(len(raw), shard[0], shard[1])
-            raw, proc = [raw[i] for i in own], [proc[i] for i in own]
-        if raw:
-            self._run_tiles(eng, img, raw, proc, geom, (num, den, RH, RW), mask, (0, 0), process_num)
-        if shard is not None:
-            num, den = self._combine_canvases(num, den)
-        if cai_mode[0] == 'r':
-            mask = self._mask((h, w), dev)
-            n2 = eng.buf('canvas.num_raw', (H, W), torch.float32)
-            d2 = eng.buf('canvas.den_raw', (H, W), torch.float32)
-            ops.call('pf_stitch_resize', num, den, RH, RW, H, W, n2, d2, st())
-            num, den = n2, d2
-            if shard is not None:
-                # the resized regular-phase canvas is identical on every rank: keep it aside so the all-gather of the
-                # random phase only sums the per-rank increments
-                n2_base, d2_base = n2.clone(), d2.clone()
-                n2.zero_()
-                d2.zero_()
-            for _ in range(int(cai_mode[1:]) // process_num):
-                ys = [random.randint(0, H - h - 1) for _ in range(process_num)]     # baseline_pretrain.py:155-156
-                x0 = random.randint(0, W - w - 1)
-                raw = [(y, x0) for y in ys]
-                if shard is not None:        # every rank draws the same boxes (same `random` state), owns a slice
-                    raw = [raw[i] for i in shard_indices(len(raw), shard[0], shard[1])]
-                if raw:
-                    self._run_tiles(eng, img, raw, raw, geom, (num, den, H, W), mask, (h, w), process_num)
-            if shard is not None:
-                num, den = self._combine_canvases(num, den, base=(n2_base, d2_base))
-        out = torch.empty_like(num)
-        ops.call('pf_stitch_finalize', num, den, ops.C.c_int64(num.numel()), out, st())
-        depth = out[None, None]
+        is_r = cai_mode[0] == 'r'
+        full = self._exchange(lambda sh: self._compute_phase(eng, 'reg', lr, img, geom, raw, process_num, sh), shard, group)
+        outs = self._stitch_phase(eng, 'reg', full, proc, world, ph, pw, mask, (0, 0), None, (RH, RW),
+                                  ('num', 'den') if is_r else ('avg',))
+        if is_r:
+            from . import ops
+            n2 = torch.empty((H, W), dtype=torch.float32, device=dev)
+            d2 = torch.empty_like(n2)
+            ops.call('pf_stitch_resize', outs['num'], outs['den'], RH, RW, H, W, n2, d2, ops.stream_ptr())
+            boxes = self._draw_random_boxes(int(cai_mode[1:]) // process_num, process_num, H, W, h, w, shard, group, dev)
+            if boxes:
+                mask_r = self._mask((h, w), dev)
+                full = self._exchange(lambda sh: self._compute_phase(eng, 'rnd', lr, img, geom, boxes, process_num, sh),
+                                      shard, group)
+                outs = self._stitch_phase(eng, 'rnd', full, boxes, world, ph, pw, mask_r, (h, w), (n2, d2), (H, W),
+                                          ('avg',))
+            else:
+                outs = {'avg': n2 / d2}
+        depth = outs['avg'][None, None]
         return depth, {'rgb': image_lr, 'depth_pred': depth, 'depth_gt': depth_gt}

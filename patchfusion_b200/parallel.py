@@ -4,12 +4,12 @@ The reference only replicates whole images over ranks (`tools/test.py:219-229`);
 sharded.  Tiles are independent given the per-image coarse outputs and the stitch is a weighted sum, so two
 decompositions are offered:
 
-* images-per-rank (bench.py default, weak scaling): every rank runs whole images; one `all_gather` assembles the
-  batch of depth canvases.
-* tiles-per-rank (`PatchFusion.forward(..., shard=(rank, world))`): coarse branch + G2L are replicated (1.3 TF, a
-  third of one tile - cheaper than broadcasting 117 MB of taps), tile i of the flattened pass list goes to rank
-  i % world, each rank scatter-accumulates its tiles into local (num, den) canvases and ONE all-gather of the
-  stacked canvases + a fixed-order sum reproduces the single-GPU canvas up to fp32 summation order.
+* images-per-rank (bench.py `value`, weak scaling): every rank runs whole images; no data-path collective.
+* tiles-per-rank (`PatchFusion.forward(..., shard=(rank, world))`): coarse branch + G2L are replicated
+  (1.3 TF, a third of one tile - cheaper than broadcasting 117 MB of taps), tile i of the flattened pass list goes to
+  rank i % world, each rank writes its fused predictions into a block [ceil(n / world), ph, pw] and ONE all-gather of
+  those blocks (5.7 MB per rank for 4K P49) lets every rank run the deterministic stitch (pf_stitch_gather) over the
+  global tile list: the canvas is bit-identical to the single-device one for any world size.
 """
 import torch
 
@@ -24,22 +24,31 @@ def shard_counts(n_items, world):
     return [len(range(r, n_items, world)) for r in range(world)]
 
 
-def gather_canvases(num, den, group=None):
-    """all_gather the per-rank (num, den) canvases -> [world, 2, H, W] on every rank (one collective)."""
+def slot_table(n_items, world):
+    """Row of global item i inside the all-gathered blocks [world * ceil(n / world), ...]: rank-major, then the
+    item's position in its rank's block."""
+    per = max(-(-n_items // world), 1)
+    return [(i % world) * per + i // world for i in range(n_items)]
+
+
+def gather_blocks(block, world, group=None):
+    """all_gather the per-rank prediction blocks -> [world * rows, ...] on every rank (the one collective)."""
     import torch.distributed as dist
-    world = dist.get_world_size(group)
-    mine = torch.stack([num, den]).contiguous()
-    stack = torch.empty((world,) + tuple(mine.shape), dtype=mine.dtype, device=mine.device)
+    assert dist.get_world_size(group) == world
+    block = block.contiguous()
+    full = torch.empty((world * block.shape[0],) + tuple(block.shape[1:]), dtype=block.dtype, device=block.device)
     if dist.get_backend(group) == 'nccl':
-        dist.all_gather_into_tensor(stack.view(-1), mine.view(-1), group=group)
+        dist.all_gather_into_tensor(full, block, group=group)
     else:                                   # gloo (CPU tests): list form
-        dist.all_gather(list(stack.unbind(0)), mine, group=group)
-    return stack
+        dist.all_gather(list(full.view((world,) + tuple(block.shape)).unbind(0)), block, group=group)
+    return full
 
 
-def reduce_canvases_reference(stack):
-    """torch restatement of pf_stitch_reduce (used by the CPU gloo test): fixed rank-order sum."""
-    out = stack[0].clone()
-    for r in range(1, stack.shape[0]):
-        out += stack[r]
-    return out[0], out[1]
+def stitch_reference(full, origins, slots, mask, shape):
+    """torch restatement of pf_stitch_gather (CPU gloo test): fixed tile-list order, one accumulation per tile."""
+    num, den = torch.zeros(shape), torch.zeros(shape)
+    th, tw = mask.shape
+    for (y, x), s in zip(origins, slots):
+        num[y:y + th, x:x + tw] += mask * full[s]
+        den[y:y + th, x:x + tw] += mask
+    return num, den

@@ -53,6 +53,17 @@ def branch_hparams(branch_cfg):
         raise ValueError("bin_centers_type should be one of 'normed', 'softplus', 'hybrid1', 'hybrid2'")
     if hp['bin_centers_type'] != 'softplus':
         raise NotImplementedError("only bin_centers_type='softplus' (every shipped PatchFusion config) is built")
+    # config fields that change the reference's arithmetic (zoedepth_v1.py:41-42 constructor defaults): honour the
+    # ones the kernels implement, refuse the rest instead of silently computing something else
+    hp['attractor_kind'] = _get(branch_cfg, 'attractor_kind', 'sum')
+    hp['attractor_type'] = _get(branch_cfg, 'attractor_type', 'exp')
+    if hp['attractor_kind'] not in ('mean', 'sum') or hp['attractor_type'] not in ('inv', 'exp'):
+        raise ValueError('attractor_kind must be mean|sum and attractor_type inv|exp')
+    if _get(branch_cfg, 'inverse_midas', False):
+        raise NotImplementedError('inverse_midas=True (zoedepth_v1.py:198-202) is not built: no PatchFusion config sets it')
+    if _get(branch_cfg, 'do_resize', False):
+        raise NotImplementedError('do_resize=True (depth_anything.py:177-190 resizer) is not built: PatchFusion feeds '
+                                  'tiles already at patch_process_shape')
     return hp
 
 

@@ -224,6 +224,64 @@ def test_stitch(cuda):
     check('stitch (resize + random tile)', out2, ra.avg, 1e-5)
 
 
+def test_stitch_gather_deterministic(cuda):
+    """pf_stitch_gather (the product path's stitch): equals the literal sequential RunningAverage to fp32 rounding, is
+    bit-identical under any permutation of where the predictions sit (slot table = the gathered per-rank blocks), and
+    continues from resized base canvases for the random phase."""
+    from patchfusion_b200 import ops
+    from patchfusion_b200.parallel import slot_table
+    from oracle import pf_oracle as po
+    g = _gen(18)
+    CH, CW, th, tw = 784, 1036, 392, 518
+    mask = torch.rand(th, tw, device=cuda, generator=g) + 1e-3
+    org = [(0, 0), (0, 518), (392, 0), (392, 518), (0, 259), (392, 259), (196, 0), (196, 518), (196, 259)]
+    n = len(org)
+    tiles = torch.rand(n, th, tw, device=cuda, generator=g)
+
+    def gather(preds, slots, up=(0, 0), msk=mask, base=(None, None), shape=(CH, CW), want=('num', 'den', 'avg')):
+        tab = torch.tensor([(y, x, s_) for (y, x), s_ in zip(org_l, slots)], dtype=torch.int32, device=cuda)
+        o = {k: torch.empty(shape, device=cuda) for k in want}
+        ops.call('pf_stitch_gather', preds, tab, len(slots), th, tw, msk, up[0], up[1], base[0], base[1], shape[0],
+                 shape[1], o.get('num'), o.get('den'), o.get('avg'), ops.stream_ptr())
+        return o
+
+    org_l = org
+    a = gather(tiles, list(range(n)))
+    # sharded layout: world 4, blocks of ceil(9/4)=3 rows, padding rows NaN
+    world, per = 4, 3
+    full = torch.full((world * per, th, tw), float('nan'), device=cuda)
+    slots = slot_table(n, world)
+    for i, s_ in enumerate(slots):
+        full[s_] = tiles[i]
+    b = gather(full, slots)
+    assert torch.equal(a['avg'], b['avg']) and torch.equal(a['num'], b['num']) and torch.equal(a['den'], b['den'])
+    cnt, acc = torch.zeros(CH, CW, device=cuda), torch.zeros(CH, CW, device=cuda)
+    for (y, x), d in zip(org[:4], tiles[:4]):
+        cnt[y:y + th, x:x + tw] = mask
+        acc[y:y + th, x:x + tw] = d * mask
+    ra = po.RunningAverage(acc, cnt)
+    for (y, x), d in zip(org[4:], tiles[4:]):
+        c2, a2 = torch.zeros(CH, CW, device=cuda), torch.zeros(CH, CW, device=cuda)
+        c2[y:y + th, x:x + tw] = mask
+        a2[y:y + th, x:x + tw] = d * mask
+        ra.update(a2, c2)
+    check('stitch gather (regular, 9 tiles)', a['avg'], ra.avg, 1e-5)
+    # random phase on top of the resized canvases
+    OH, OW, uh, uw = 1080, 1920, 540, 960
+    n2, d2 = torch.empty(OH, OW, device=cuda), torch.empty(OH, OW, device=cuda)
+    ops.call('pf_stitch_resize', a['num'], a['den'], CH, CW, OH, OW, n2, d2, ops.stream_ptr())
+    mask2 = torch.rand(uh, uw, device=cuda, generator=g) + 1e-3
+    org_l = [(100, 333), (400, 333), (17, 333)]
+    r = gather(tiles[:3].contiguous(), [0, 1, 2], up=(uh, uw), msk=mask2, base=(n2, d2), shape=(OH, OW), want=('avg',))
+    ra.resize((OH, OW))
+    for (y, x), d in zip(org_l, F.interpolate(tiles[:3, None], (uh, uw))[:, 0]):
+        c3, a3 = torch.zeros(OH, OW, device=cuda), torch.zeros(OH, OW, device=cuda)
+        c3[y:y + uh, x:x + uw] = mask2
+        a3[y:y + uh, x:x + uw] = d * mask2
+        ra.update(a3, c3)
+    check('stitch gather (resize + 3 random tiles)', r['avg'], ra.avg, 1e-5)
+
+
 def test_ingest_and_u16_writer(cuda):
     """the callers either side of the path: bicubic align_corners ingest and the uint16 depth writer"""
     from patchfusion_b200 import imageio

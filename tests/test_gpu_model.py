@@ -72,7 +72,7 @@ def test_coarse_branch_taps(cuda, setup):
           (err, err / MAX_DEPTH, d_o.min().item(), d_o.max().item()))
     assert not bad, bad
     assert err / MAX_DEPTH < 1e-3
-    assert err / (d_o.max() - d_o.min()).item() < 5e-2, 'error must also be small against the output range'
+    assert err / (d_o.max() - d_o.min()).item() < 2e-2, 'error must also be small against the output range'
     # reference fixture (strided sample of the real reference's output)
     st = s['case']['sample_stride']
     g = torch.tensor(s['gold']['coarse_depth'])
@@ -152,12 +152,12 @@ def test_infer_vs_reference_fixture(cuda, setup, mode):
           (mode, err, err / MAX_DEPTH, g.min().item(), g.max().item()))
     assert torch.isfinite(y).all()
     assert err / MAX_DEPTH < 1e-3
-    assert err / (g.max() - g.min()).item() < 5e-2, 'error must also be small against the output range'
+    assert err / (g.max() - g.min()).item() < 2e-2, 'error must also be small against the output range'
 
 
 def test_micro_batch_grouping_invariance(cuda, setup):
-    """Tiles are independent: m2 with process_num 2 / 4 / 9 (different micro-batch sizes, graphs and buffer sets)
-    gives the same canvas up to the fp32 order of the stitch's atomic adds."""
+    """Tiles are independent and the stitch sums in a fixed order: m2 with process_num 2 / 4 / 9 (different
+    micro-batch sizes, graphs and buffer sets) gives the same canvas bit for bit."""
     s = setup
     model, img = s['model'], s['img']
     lr = model.resizer(img)
@@ -168,16 +168,13 @@ def test_micro_batch_grouping_invariance(cuda, setup):
     for y in outs[1:]:
         err = (y - outs[0]).abs().max().item()
         print('process_num invariance: max diff %.3e' % err)
-        assert err < 2e-3        # bf16 GEMM results are batch-size independent; only tile->CTA order may differ
+        assert err == 0.0
 
 
-def test_vitl_full_size_tile_against_oracle(cuda):
-    """The flagship configuration (Depth-Anything-vitl, 4K, 4x4 split): coarse branch + two fused tiles through the
-    CUDA path against the oracle restatement executed by torch on the GPU in fp32 (TF32 off) - the CPU oracle needs
-    ~100 s per vitl tile.  Plus a size-independent property at full size: a canvas stitched from constant tiles is
-    that constant (partition of unity of the blend weights over all 49 tiles)."""
+def test_vitl_coarse_and_two_tiles_with_taps(cuda):
+    """Depth-Anything-vitl: coarse branch taps, G2L maps and two fused tiles against the GPU-executed oracle (the full
+    P16 / P49 canvases are in tests/test_gpu_configs.py)."""
     from oracle import pf_oracle as po
-    from patchfusion_b200 import ops
     from patchfusion_b200.configs import depth_anything_patchfusion
     from patchfusion_b200.model import PatchFusion
     from patchfusion_b200.params import synthetic_state_dict
@@ -203,37 +200,22 @@ def test_vitl_full_size_tile_against_oracle(cuda):
     cd, cf = eng.branch('coarse', lr.contiguous())
     err_c = (cd[0] - cd_o[0, 0]).abs().max().item()
     print('vitl coarse depth max-abs %.3e (range %.3f..%.3f)' % (err_c, cd_o.min().item(), cd_o.max().item()))
-    assert err_c / MAX_DEPTH < 1e-3 and err_c / (cd_o.max() - cd_o.min()).item() < 5e-2
+    assert err_c / MAX_DEPTH < 1e-3 and err_c / (cd_o.max() - cd_o.min()).item() < 2e-2
     for a, b in zip(cf, cf_o):
         e = rel_err(a.t[..., :a.C].float().permute(0, 3, 1, 2), b)
         assert e < 3e-2, e
     model._coarse = (cd[0], cf, eng.g2l(cf))
     for a, b in zip(model._coarse[2], g2l_o):
         assert rel_err(a.t[..., :a.C].float().permute(0, 3, 1, 2), b) < 4e-2
-    num = torch.zeros(P[0] * 4, P[1] * 4, device=cuda)
-    den = torch.zeros_like(num)
-    io = model._tile_io(eng, 2)
-    io['raw'].copy_(torch.tensor(raw, dtype=torch.int32))
-    io['dst'].copy_(torch.tensor([(392, 518), (588, 777)], dtype=torch.int32))
+    io_raw = torch.tensor(raw, dtype=torch.int32, device=cuda)
     fx, fy = np.float32(1 / W * P[1]), np.float32(1 / H * P[0])
-    io['boxes'].copy_(torch.tensor([[x * fx, y * fy, (x + w) * fx, (y + h) * fy] for (y, x) in raw], dtype=torch.float32))
-    mask = model._mask(P, cuda)
-    model._tiles_stage(eng, img[0].contiguous(), 2, (H, W, h, w, P[0], P[1]), (num, den, P[0] * 4, P[1] * 4), mask, (0, 0))
-    pred = eng.bufs[('fus.head.depth', (2, P[0], P[1]), torch.float32)]
+    boxes = torch.tensor([[x * fx, y * fy, (x + w) * fx, (y + h) * fy] for (y, x) in raw], dtype=torch.float32, device=cuda)
+    pred = torch.empty((2, P[0], P[1]), device=cuda)
+    fine = model._fine_stage(eng, img[0].contiguous(), 2, (H, W, h, w, P[0], P[1]), io_raw)
+    model._fusion_stage(eng, fine, boxes, pred)
     err = (pred - fu_o[:, 0]).abs().max().item()
     print('vitl fused tiles max-abs %.3e (range %.3f..%.3f)' % (err, fu_o.min().item(), fu_o.max().item()))
-    assert err / MAX_DEPTH < 1e-3 and err / (fu_o.max() - fu_o.min()).item() < 5e-2
-    # partition of unity at the full P49 geometry
-    tcf = po.prepare_tile_cfg((H, W), (4, 4), P)
-    plan = [t[1] for p in po.tile_plan(tcf, P, 'm2') for t in p]
-    assert len(plan) == 49
-    n2, d2 = torch.zeros_like(num), torch.zeros_like(den)
-    const = torch.full((49, P[0], P[1]), 3.25, device=cuda)
-    org = torch.tensor(plan, dtype=torch.int32, device=cuda)
-    ops.call('pf_stitch_accumulate', n2, d2, P[0] * 4, P[1] * 4, const, 49, P[0], P[1], org, mask, 0, 0, ops.stream_ptr())
-    out = torch.empty_like(n2)
-    ops.call('pf_stitch_finalize', n2, d2, ops.C.c_int64(n2.numel()), out, ops.stream_ptr())
-    assert (out - 3.25).abs().max().item() < 1e-5
+    assert err / MAX_DEPTH < 1e-3 and err / (fu_o.max() - fu_o.min()).item() < 2e-2
 
 
 def _cuda_oracle(cfg, sd, cuda):
@@ -258,7 +240,7 @@ def test_tile_cfg_override_4x4_and_r_mode(cuda, setup):
         assert got.shape == want.shape
         err = (got - want).abs().max().item()
         print('%s 4x4: max-abs %.3e (range %.3f..%.3f)' % (mode, err, want.min().item(), want.max().item()))
-        assert err / MAX_DEPTH < 1e-3 and err / (want.max() - want.min()).item() < 5e-2
+        assert err / MAX_DEPTH < 1e-3 and err / (want.max() - want.min()).item() < 2e-2
     with pytest.raises(AssertionError):
         model(mode='infer', image_lr=lr, image_hr=img, tile_cfg={'image_raw_shape': [1080, 1920], 'patch_split_num': [7, 4]})
 
@@ -283,7 +265,7 @@ def test_vitb_branch(cuda):
         assert rel_err(a.t[..., :a.C].float().permute(0, 3, 1, 2), b) < 3e-2
     err = (d - d_o[:, 0]).abs().max().item()
     print('vitb fine depth max-abs %.3e (range %.3f..%.3f)' % (err, d_o.min().item(), d_o.max().item()))
-    assert err / MAX_DEPTH < 1e-3 and err / (d_o.max() - d_o.min()).item() < 5e-2
+    assert err / MAX_DEPTH < 1e-3 and err / (d_o.max() - d_o.min()).item() < 2e-2
 
 
 def test_stage_level_api(cuda, setup):

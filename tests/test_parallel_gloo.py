@@ -1,5 +1,5 @@
-"""world_size-2 gloo test (CPU) of the tile-sharding host logic: ownership plan, the single all-gather of the
-(num, den) canvases and the fixed-order reduction reproduce the single-process stitch."""
+"""world_size-2 gloo test (CPU) of the tile-sharding host logic: ownership plan, slot table, the single all-gather of
+the per-rank prediction blocks and the fixed-order stitch reproduce the single-process canvas BIT-EXACTLY."""
 import os
 
 import pytest
@@ -7,29 +7,25 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from patchfusion_b200.parallel import gather_canvases, reduce_canvases_reference, shard_counts, shard_indices
+from patchfusion_b200.parallel import gather_blocks, shard_counts, shard_indices, slot_table, stitch_reference
 
 pytestmark = pytest.mark.timeout(300)
 
 
 def test_shard_plan():
-    for n, w in [(49, 8), (16, 8), (225, 8), (9, 2), (3, 4)]:
+    for n, w in [(49, 8), (16, 8), (225, 8), (9, 2), (3, 4), (128, 8)]:
         owned = [shard_indices(n, r, w) for r in range(w)]
         flat = sorted(i for o in owned for i in o)
         assert flat == list(range(n))
         c = shard_counts(n, w)
         assert max(c) - min(c) <= 1 and sum(c) == n
+        # slot table: item i sits at row (i // w) of rank (i % w)'s block
+        per = -(-n // w)
+        slots = slot_table(n, w)
+        assert len(set(slots)) == n
+        for r in range(w):
+            assert [slots[i] for i in owned[r]] == [r * per + j for j in range(len(owned[r]))]
     assert shard_counts(49, 8) == [7, 6, 6, 6, 6, 6, 6, 6]
-
-
-def _stitch(tiles, origins, mask, shape, idx):
-    num, den = torch.zeros(shape), torch.zeros(shape)
-    th, tw = mask.shape
-    for i in idx:
-        y, x = origins[i]
-        num[y:y + th, x:x + tw] += mask * tiles[i]
-        den[y:y + th, x:x + tw] += mask
-    return num, den
 
 
 def _worker(rank, world, port, out):
@@ -39,16 +35,21 @@ def _worker(rank, world, port, out):
     g = torch.Generator().manual_seed(0)
     th, tw, shape = 24, 32, (48, 64)
     origins = [(0, 0), (0, 32), (24, 0), (24, 32), (0, 16), (24, 16), (12, 0), (12, 32), (12, 16)]
-    tiles = torch.rand(len(origins), th, tw, generator=g)
+    n = len(origins)
+    tiles = torch.rand(n, th, tw, generator=g)
     mask = torch.rand(th, tw, generator=g) + 1e-3
-    num, den = _stitch(tiles, origins, mask, shape, shard_indices(len(origins), rank, world))
-    stack = gather_canvases(num, den)
-    assert stack.shape == (world, 2) + shape
-    n, d = reduce_canvases_reference(stack)
-    full_n, full_d = _stitch(tiles, origins, mask, shape, range(len(origins)))
-    err = ((n / d) - (full_n / full_d)).abs().max().item()
+    own = shard_indices(n, rank, world)
+    per = -(-n // world)
+    block = torch.full((per, th, tw), float('nan'))           # padding rows must never be read
+    for j, i in enumerate(own):
+        block[j] = tiles[i]
+    full = gather_blocks(block, world)
+    assert full.shape == (world * per, th, tw)
+    num, den = stitch_reference(full, origins, slot_table(n, world), mask, shape)
+    full_n, full_d = stitch_reference(tiles, origins, list(range(n)), mask, shape)
+    same = torch.equal(num, full_n) and torch.equal(den, full_d)
     if rank == 0:
-        out.put(err)
+        out.put(same)
     dist.barrier()
     dist.destroy_process_group()
 
@@ -63,4 +64,4 @@ def test_two_rank_gather_matches_single_process():
     for p in procs:
         p.join(120)
         assert p.exitcode == 0
-    assert out.get(timeout=5) < 1e-6
+    assert out.get(timeout=5) is True

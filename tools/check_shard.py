@@ -29,7 +29,7 @@ for mode in ('m1', 'm2', 'r4'):
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     if rank == 0:
         print('%s: world %d  max|sharded - single| = %.3e (range %.3f..%.3f)' % (mode, world, t.item(), ref.min().item(), ref.max().item()), flush=True)
-    ok = ok and t.item() < 1e-5
+    ok = ok and t.item() == 0.0          # deterministic stitch over gathered prediction blocks: bit-identical
 dist.barrier()
 dist.destroy_process_group()
 sys.exit(0 if ok else 1)
