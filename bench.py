@@ -368,6 +368,7 @@ def main():
         local_step(img_dev)                 # no collective here: only rank 0 runs this pass
         torch.cuda.synchronize()
         prof_records = lib.PROFILER.records
+        prof_labels = lib.PROFILER.labels
         lib.PROFILER = None
     barrier()
 
@@ -408,6 +409,17 @@ def main():
                 whole_step_tflops=(tps / world * F_TILE[enc] + tps / world / n_tiles * F_IMAGE[enc]) / 1e12)
     prof = fam
     if args.profile:
+        # per launch-shape table (label -> launches, ms, TF/s), slowest first; also written to gpurun_out/
+        by = {}
+        for (f_, fl, e0, e1), lab in zip(prof_records, prof_labels):
+            d_ = by.setdefault(lab, [0, 0.0, 0.0])
+            d_[0] += 1; d_[1] += e0.elapsed_time(e1); d_[2] += fl
+        rows_ = sorted(by.items(), key=lambda kv: -kv[1][1])
+        os.makedirs(os.path.join(ROOT, 'gpurun_out'), exist_ok=True)
+        json.dump([dict(label=k_, launches=v[0], ms=v[1], tflops=v[2] / max(v[1], 1e-9) / 1e9) for k_, v in rows_],
+                  open(os.path.join(ROOT, 'gpurun_out', 'profile_shapes.json'), 'w'), indent=1)
+        for k_, v in rows_[:60]:
+            sys.stderr.write('%-64s %5d x %8.3f ms %8.1f TF/s\n' % (k_, v[0], v[1], v[2] / max(v[1], 1e-9) / 1e9))
         for k_, v in sorted(prof.items(), key=lambda kv: -kv[1]['ms']):
             sys.stderr.write('%-26s %8.2f ms %6d launches %8.1f TF/s\n' % (k_, v['ms'], v['launches'],
                                                                          v['flops'] / max(v['ms'], 1e-9) / 1e9))

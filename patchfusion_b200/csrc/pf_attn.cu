@@ -1,14 +1,21 @@
 // Fused attention for the DINOv2 blocks: softmax(Q K^T * scale) V without materialising the (B,heads,N,N) score
 // tensor the reference builds (`dinov2/layers/attention.py:53-59`).  head_dim = 64, no mask, N = 1037 tokens.
 //
-// One CTA per (128-query block, head, image).  Both contractions run on tcgen05 with fp32 accumulators in TMEM:
-//   S[128x128]   = Q[128x64] . K_j[128x64]^T          (TMA loads straight from the qkv GEMM output, K-major)
-//   Otmp[128x64] = P[128x128] . V_j[128x64]           (P: bf16 written by the softmax warps into a SWIZZLE_128B
-//                                                       tile; V^T tiles come from the transposed copy the qkv GEMM
-//                                                       epilogue writes, so both operands stay K-major)
-// Warps 0-3 own one query row per thread (TMEM lane == row): online softmax in fp32, P -> smem, running rescale of
-// the register-resident output.  Warp 4 = TMA producer, warp 5 = MMA issuer.  Two CTAs fit per SM (80 KB smem,
-// 256 TMEM columns each) so one CTA's softmax overlaps the other's MMAs.
+// Persistent kernel, one CTA per SM, work item = (image b, head h, PAIR of 128-query tiles).  Both contractions run on
+// tcgen05 with every accumulator in tensor memory (512 columns):
+//   S_t[128x128] = Q_t[128x64] . K_j[128x64]^T     t = 0,1   (TMA loads straight from the qkv GEMM output, K-major)
+//   O_t[128x64] += P_t[128x128] . V_j[128x64]      P_t is the A operand IN TMEM (bf16, written by the softmax warps
+//                                                  with tcgen05.st - it never touches shared memory); V^T tiles come
+//                                                  from the transposed copy the qkv GEMM epilogue writes (K-major B).
+//   TMEM columns: S_0 0..127 | S_1 128..255 | O_0 256..319 | O_1 320..383 | P_0 384..447 | P_1 448..511
+// Warps 0-3 / 4-7: softmax of Q tile 0 / 1, ONE THREAD PER QUERY ROW (TMEM lane == row): the 128 scores of a KV block
+// are read from TMEM once into registers, the S buffer is handed back to the tensor core immediately (QK^T of block
+// j+1 overlaps softmax of block j), row max by 3-input FMNMX, exp2 on MUFU for most elements and on the FMA pipe
+// (Cody-Waite + cubic, packed FFMA2) for the rest - at head_dim 64 the MUFU pipe, not the tensor pipe, bounds
+// attention - packed FADD2 row sums, bf16 P back into TMEM.  O stays in TMEM across KV blocks; it is rescaled (by
+// the row's own thread) only when the running max moves by more than 2^8 (lazy rescale with a stale max, exact after
+// the final 1/l normalisation).  Warp 8 = TMA producer, warp 9 = single-thread MMA issuer.  K_j / V_j are shared by
+// the two Q tiles.  The last KV block (1037 = 8*128 + 13 keys) runs with N = 16 / K = 16 instead of a padded 128.
 #include <stdlib.h>
 
 #include "pf_common.cuh"
@@ -16,8 +23,18 @@
 
 namespace pf {
 
-constexpr int kAttnThreads = 192;
 constexpr int kQTile = 128, kKTile = 128, kHd = 64;
+constexpr int kAttnThreads = 320;
+constexpr int kKS = 3, kVS = 3;                      // K / V smem ring depths
+constexpr int kTileBytes = 16384;
+constexpr int kOffQ = 0;                             // 2 x [128 q][64]
+constexpr int kOffK = 2 * kTileBytes;                // kKS x [128 keys][64]
+constexpr int kOffV = kOffK + kKS * kTileBytes;      // kVS x 2 x [64 d][64 keys]
+constexpr int kOffBar = kOffV + kVS * kTileBytes;
+constexpr int kAttnSmem = 1024 + kOffBar + 512;
+constexpr uint32_t kColS = 0, kColO = 256, kColP = 384;
+constexpr float kRescaleThreshold = 8.0f;            // log2 units: P stays below 2^8, far inside bf16 / fp32 range
+constexpr int kPolyPairs = 5;                        // of the 16 pairs per 32-score chunk, evaluated on the FMA pipe
 
 __device__ __forceinline__ float ex2_approx(float x) {
   float y;
@@ -25,425 +42,348 @@ __device__ __forceinline__ float ex2_approx(float x) {
   return y;
 }
 
+// 2^x for two values on the FMA/ALU pipes: n = round(x), f = x - n in [-0.5, 0.5], 2^f by a cubic minimax
+// (max rel err 7.5e-5, far below the bf16 rounding of P), exponent patched in with an integer add.  x >= -126.
+__device__ __forceinline__ uint64_t ex2_poly2(uint64_t x) {
+  float x0, x1;
+  unpack2f(x, x0, x1);
+  const uint64_t xc = pack2f(fmaxf(x0, -126.0f), fmaxf(x1, -126.0f));
+  const uint64_t magic = pack2f(12582912.0f, 12582912.0f);          // 1.5 * 2^23: low mantissa bits = round(x)
+  const uint64_t t = add2(xc, magic);
+  const uint64_t f = sub2(xc, sub2(t, magic));
+  uint64_t p = fma2(f, pack2f(0.05517164617776871f, 0.05517164617776871f), pack2f(0.2426111251115799f, 0.2426111251115799f));
+  p = fma2(p, f, pack2f(0.6932609677314758f, 0.6932609677314758f));
+  p = fma2(p, f, pack2f(0.9999280571937561f, 0.9999280571937561f));
+  float t0, t1, p0, p1;
+  unpack2f(t, t0, t1);
+  unpack2f(p, p0, p1);
+  const uint32_t r0 = __float_as_uint(p0) + (__float_as_uint(t0) << 23);
+  const uint32_t r1 = __float_as_uint(p1) + (__float_as_uint(t1) << 23);
+  return pack2(r0, r1);
+}
+
+// 32 scores of one row -> 16 packed bf16x2 probabilities; row-sum partials in two packed accumulators.
+__device__ __forceinline__ void softmax_chunk(const uint32_t (&s)[32], uint64_t sc2, uint64_t nm2, uint64_t& sum_a,
+                                              uint64_t& sum_b, uint32_t (&pk)[16]) {
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const uint64_t x = fma2(pack2(s[2 * i], s[2 * i + 1]), sc2, nm2);
+    uint64_t e;
+    // Bresenham spread of the polynomial pairs over the chunk so MUFU and FMA work interleave
+    if (((i + 1) * kPolyPairs) / 16 != (i * kPolyPairs) / 16) {
+      e = ex2_poly2(x);
+    } else {
+      float x0, x1;
+      unpack2f(x, x0, x1);
+      e = pack2f(ex2_approx(x0), ex2_approx(x1));
+    }
+    if (i & 1) sum_b = add2(sum_b, e); else sum_a = add2(sum_a, e);
+    float e0, e1;
+    unpack2f(e, e0, e1);
+    pk[i] = pack_bf16(e0, e1);
+  }
+}
+
 struct AttnParams {
   CUtensorMap tmQK;   // 3-D {2*D, seq, B}, box {64, 128, 1}
   CUtensorMap tmVt;   // 2-D {seq_pad, B*heads*64}, box {64, 64}
   int B, seq, heads, D;
+  int n_pairs, n_items;
   float scale_log2;   // scale * log2(e)
   __nv_bfloat16* out;
   int out_ld;
 };
 
-__global__ void __launch_bounds__(kAttnThreads, 2) pf_attention_kernel(const __grid_constant__ AttnParams P) {
+__global__ void __launch_bounds__(kAttnThreads, 1) pf_attention_kernel(const __grid_constant__ AttnParams P) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* sQ = smem;                    // 16 KB  [128 q][64]
-  uint8_t* sK = smem + 16384;            // 16 KB  [128 keys][64]
-  uint8_t* sV = smem + 32768;            // 16 KB  2 x [64 d][64 keys]
-  uint8_t* sP = smem + 49152;            // 32 KB  2 x [128 q][64 keys]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 81920);
+  uint8_t* sQ = smem + kOffQ;
+  uint8_t* sK = smem + kOffK;
+  uint8_t* sV = smem + kOffV;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kOffBar);
   uint64_t* q_full = bars + 0;
-  uint64_t* k_full = bars + 1;
-  uint64_t* k_empty = bars + 2;
-  uint64_t* v_full = bars + 3;
-  uint64_t* v_empty = bars + 4;
-  uint64_t* s_full = bars + 5;
-  uint64_t* p_full = bars + 6;
-  uint64_t* o_full = bars + 7;
-  uint64_t* o_empty = bars + 8;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
+  uint64_t* q_empty = bars + 1;
+  uint64_t* k_full = bars + 2;                  // [kKS]
+  uint64_t* k_empty = k_full + kKS;
+  uint64_t* v_full = k_empty + kKS;             // [kVS]
+  uint64_t* v_empty = v_full + kVS;
+  uint64_t* s_full = v_empty + kVS;             // [2]  QK^T of the tile's current block is complete
+  uint64_t* s_free = s_full + 2;                // [2]  the softmax warps hold the scores in registers
+  uint64_t* p_full = s_free + 2;                // [2]  P of the current block is in TMEM
+  uint64_t* o_done = p_full + 2;                // [2]  PV of the current block is complete
+  uint64_t* o_free = o_done + 2;                // [2]  the item's O has been read out
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_free + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int qb = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
-  const int q0 = qb * kQTile;
-  const int nkv = (P.seq + kKTile - 1) / kKTile;
-
-  if (warp == 4 && lane == 0) {
-    prefetch_tmap(&P.tmQK);
-    prefetch_tmap(&P.tmVt);
-    mbar_init(q_full, 1); mbar_init(k_full, 1); mbar_init(k_empty, 1); mbar_init(v_full, 1); mbar_init(v_empty, 1);
-    mbar_init(s_full, 1); mbar_init(p_full, 128); mbar_init(o_full, 1); mbar_init(o_empty, 128);
-    fence_barrier_init();
-  }
-  if (warp == 5) tmem_alloc(tmem_slot, 256);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tmem_S = tmem_base, tmem_O = tmem_base + 128;
-  pdl_wait();
-
-  if (warp == 4) {
-    if (lane == 0) {
-      mbar_expect_tx(q_full, 16384);
-      tma_load_3d(sQ, &P.tmQK, q_full, h * kHd, q0, b);
-      for (int j = 0; j < nkv; ++j) {
-        const uint32_t ph = j & 1;
-        mbar_wait(k_empty, ph ^ 1);
-        mbar_expect_tx(k_full, 16384);
-        tma_load_3d(sK, &P.tmQK, k_full, P.D + h * kHd, j * kKTile, b);
-        mbar_wait(v_empty, ph ^ 1);
-        mbar_expect_tx(v_full, 16384);
-        tma_load_2d(sV, &P.tmVt, v_full, j * kKTile, (b * P.heads + h) * kHd);
-        tma_load_2d(sV + 8192, &P.tmVt, v_full, j * kKTile + 64, (b * P.heads + h) * kHd);
-      }
-    }
-  } else if (warp == 5) {
-    if (lane == 0) {
-      const uint32_t idesc_s = umma_idesc_bf16(128, 128);
-      const uint32_t idesc_o = umma_idesc_bf16(128, 64);
-      const uint64_t dq = umma_desc_k128(smem_u32(sQ));
-      const uint64_t dk = umma_desc_k128(smem_u32(sK));
-      const uint64_t dv0 = umma_desc_k128(smem_u32(sV)), dv1 = umma_desc_k128(smem_u32(sV + 8192));
-      const uint64_t dp0 = umma_desc_k128(smem_u32(sP)), dp1 = umma_desc_k128(smem_u32(sP + 16384));
-      mbar_wait(q_full, 0);
-      mbar_wait(k_full, 0);
-      tc_fence_after();
-#pragma unroll
-      for (int k = 0; k < 4; ++k) umma_bf16(tmem_S, dq + 2 * k, dk + 2 * k, idesc_s, k != 0);
-      umma_commit(k_empty);
-      umma_commit(s_full);
-      for (int j = 0; j < nkv; ++j) {
-        const uint32_t ph = j & 1;
-        mbar_wait(p_full, ph);
-        mbar_wait(v_full, ph);
-        mbar_wait(o_empty, ph ^ 1);
-        tc_fence_after();
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          const uint64_t pa = (k < 4 ? dp0 : dp1) + 2 * (k & 3);
-          const uint64_t vb = (k < 4 ? dv0 : dv1) + 2 * (k & 3);
-          umma_bf16(tmem_O, pa, vb, idesc_o, k != 0);
-        }
-        umma_commit(v_empty);
-        umma_commit(o_full);
-        if (j + 1 < nkv) {
-          mbar_wait(k_full, ph ^ 1);
-          tc_fence_after();
-#pragma unroll
-          for (int k = 0; k < 4; ++k) umma_bf16(tmem_S, dq + 2 * k, dk + 2 * k, idesc_s, k != 0);
-          umma_commit(k_empty);
-          umma_commit(s_full);
-        }
-      }
-    }
-  } else {
-    // ===================== softmax / output warps: thread == query row =====================
-    const int r = warp * 32 + lane;
-    const uint32_t lane_sel = static_cast<uint32_t>(warp * 32) << 16;
-    float o_acc[kHd];
-#pragma unroll
-    for (int i = 0; i < kHd; ++i) o_acc[i] = 0.0f;
-    float m_run = -INFINITY, l_run = 0.0f;
-    for (int j = 0; j < nkv; ++j) {
-      const uint32_t ph = j & 1;
-      const int kvalid = min(kKTile, P.seq - j * kKTile);   // keys of this block that exist
-      mbar_wait(s_full, ph);
-      tc_fence_after();
-      // pass 1: row max of the raw scores (scale > 0, applied once afterwards).  TMEM loads are software
-      // pipelined: chunk i+1 is in flight while chunk i is consumed.
-      // four independent max / sum chains: the serial 128-long FMNMX / FADD dependency chains were the critical
-      // path of a softmax warp (2 warps per scheduler cannot hide 4-cycle-latency chains)
-      float mr[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
-      const bool full = kvalid == kKTile;
-      uint32_t va[32], vb[32];
-      tmem_ld32(tmem_S + lane_sel, va);
-      tmem_ld_wait();
-#pragma unroll
-      for (int c2 = 0; c2 < kKTile / 32; ++c2) {
-        uint32_t (&cur)[32] = (c2 & 1) ? vb : va;
-        uint32_t (&nxt)[32] = (c2 & 1) ? va : vb;
-        // after the last score chunk, prefetch chunk 0 again for pass 2
-        tmem_ld32(tmem_S + lane_sel + ((c2 + 1) & 3) * 32, nxt);
-        const int cb = c2 * 32;
-        if (full) {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) mr[i & 3] = fmaxf(mr[i & 3], __uint_as_float(cur[i]));
-        } else {
-#pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (cb + i < kvalid) mr[i & 3] = fmaxf(mr[i & 3], __uint_as_float(cur[i]));
-        }
-        tmem_ld_wait();
-      }
-      const float m_raw = fmaxf(fmaxf(mr[0], mr[1]), fmaxf(mr[2], mr[3]));
-      const float m_new = fmaxf(m_run, m_raw * P.scale_log2);
-      const float alpha = ex2_approx(m_run - m_new);
-      float ls[4] = {0.f, 0.f, 0.f, 0.f};
-      // pass 2: p = 2^(s*scale - m) (one FFMA + one MUFU per score), bf16 pairs -> swizzled smem tile.
-      // (va holds chunk 0 again at this point)
-#pragma unroll
-      for (int c2 = 0; c2 < kKTile / 32; ++c2) {
-        uint32_t (&cur)[32] = (c2 & 1) ? vb : va;
-        uint32_t (&nxt)[32] = (c2 & 1) ? va : vb;
-        if (c2 + 1 < kKTile / 32) tmem_ld32(tmem_S + lane_sel + (c2 + 1) * 32, nxt);
-        const int cb = c2 * 32;
-        float p[32];
-        if (full) {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            p[i] = ex2_approx(fmaf(__uint_as_float(cur[i]), P.scale_log2, -m_new));
-            ls[i & 3] += p[i];
-          }
-        } else {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            float e = ex2_approx(fmaf(__uint_as_float(cur[i]), P.scale_log2, -m_new));
-            p[i] = (cb + i < kvalid) ? e : 0.0f;
-            ls[i & 3] += p[i];
-          }
-        }
-        uint8_t* sub = sP + (cb >> 6) * 16384 + r * 128;
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          const int chunk = ((cb & 63) >> 3) + g;                 // 16-byte chunk index inside the 128-B row
-          uint4 pk = make_uint4(pack_bf16(p[g * 8 + 0], p[g * 8 + 1]), pack_bf16(p[g * 8 + 2], p[g * 8 + 3]),
-                                pack_bf16(p[g * 8 + 4], p[g * 8 + 5]), pack_bf16(p[g * 8 + 6], p[g * 8 + 7]));
-          *reinterpret_cast<uint4*>(sub + ((chunk ^ (r & 7)) << 4)) = pk;
-        }
-        if (c2 + 1 < kKTile / 32) tmem_ld_wait();
-      }
-      l_run = l_run * alpha + ((ls[0] + ls[1]) + (ls[2] + ls[3]));
-      m_run = m_new;
-      fence_proxy_async_smem();      // generic-proxy smem writes -> visible to the tensor core (async proxy)
-      tc_fence_before();
-      mbar_arrive(p_full);
-      // accumulate this block's P.V
-      mbar_wait(o_full, ph);
-      tc_fence_after();
-      tmem_ld32(tmem_O + lane_sel, va);
-      tmem_ld32(tmem_O + lane_sel + 32, vb);
-      tmem_ld_wait();
-#pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        o_acc[i] = fmaf(o_acc[i], alpha, __uint_as_float(va[i]));
-        o_acc[32 + i] = fmaf(o_acc[32 + i], alpha, __uint_as_float(vb[i]));
-      }
-      tc_fence_before();
-      mbar_arrive(o_empty);
-    }
-    const int tok = q0 + r;
-    if (tok < P.seq) {
-      const float inv = 1.0f / l_run;
-      __nv_bfloat16* op = P.out + (static_cast<long long>(b) * P.seq + tok) * P.out_ld + h * kHd;
-#pragma unroll
-      for (int i = 0; i < kHd; i += 8) {
-        uint4 pk = make_uint4(pack_bf16(o_acc[i] * inv, o_acc[i + 1] * inv), pack_bf16(o_acc[i + 2] * inv, o_acc[i + 3] * inv),
-                              pack_bf16(o_acc[i + 4] * inv, o_acc[i + 5] * inv), pack_bf16(o_acc[i + 6] * inv, o_acc[i + 7] * inv));
-        *reinterpret_cast<uint4*>(op + i) = pk;
-      }
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 5) {
-    tc_fence_after();
-    tmem_dealloc(tmem_base, 256);
-  }
-}
-
-// ------------------------------------------------------------------------------------------------------------
-// v2: same pipeline, but EIGHT softmax warps per CTA (16 per SM): the two warps of a TMEM lane quadrant split every
-// query row - warp half hh owns score columns [64 hh, 64 hh + 64) and output columns [32 hh, 32 hh + 32).  The row
-// maximum is exchanged through shared memory once per KV block (one 64-thread named barrier), the row sums are
-// combined once at the end.  Twice the warps hide the tcgen05.ld / MUFU / FMA latencies that bounded v1 (ncu: 30 %
-// long-scoreboard + 22 % wait stalls at 2 softmax warps per scheduler), and each thread keeps only 32 + 32 registers
-// of row state.
-constexpr int kAttn2Threads = 320;
-
-__global__ void __launch_bounds__(kAttn2Threads, 2) pf_attention_kernel_v2(const __grid_constant__ AttnParams P) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* sQ = smem;
-  uint8_t* sK = smem + 16384;
-  uint8_t* sV = smem + 32768;
-  uint8_t* sP = smem + 49152;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 81920);
-  uint64_t* q_full = bars + 0;
-  uint64_t* k_full = bars + 1;
-  uint64_t* k_empty = bars + 2;
-  uint64_t* v_full = bars + 3;
-  uint64_t* v_empty = bars + 4;
-  uint64_t* s_full = bars + 5;
-  uint64_t* p_full = bars + 6;
-  uint64_t* o_full = bars + 7;
-  uint64_t* o_empty = bars + 8;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
-  float* xch = reinterpret_cast<float*>(smem + 81920 + 128);      // [2 parities][2 halves][128 rows]
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int qb = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
-  const int q0 = qb * kQTile;
-  const int nkv = (P.seq + kKTile - 1) / kKTile;
+  const int seq = P.seq;
+  const int nkv = (seq + kKTile - 1) / kKTile;
+  pdl_launch_dependents();
 
   if (warp == 8 && lane == 0) {
     prefetch_tmap(&P.tmQK);
     prefetch_tmap(&P.tmVt);
-    mbar_init(q_full, 1); mbar_init(k_full, 1); mbar_init(k_empty, 1); mbar_init(v_full, 1); mbar_init(v_empty, 1);
-    mbar_init(s_full, 1); mbar_init(p_full, 256); mbar_init(o_full, 1); mbar_init(o_empty, 256);
+    mbar_init(q_full, 1); mbar_init(q_empty, 1);
+    for (int s = 0; s < kKS; ++s) { mbar_init(&k_full[s], 1); mbar_init(&k_empty[s], 1); }
+    for (int s = 0; s < kVS; ++s) { mbar_init(&v_full[s], 1); mbar_init(&v_empty[s], 1); }
+    for (int t = 0; t < 2; ++t) {
+      mbar_init(&s_full[t], 1); mbar_init(&s_free[t], 4); mbar_init(&p_full[t], 4);
+      mbar_init(&o_done[t], 1); mbar_init(&o_free[t], 4);
+    }
     fence_barrier_init();
   }
-  if (warp == 9) tmem_alloc(tmem_slot, 256);
+  if (warp == 9) tmem_alloc(tmem_slot, 512);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tmem_S = tmem_base, tmem_O = tmem_base + 128;
   pdl_wait();
 
   if (warp == 8) {
+    // ===================== TMA producer =====================
     if (lane == 0) {
-      mbar_expect_tx(q_full, 16384);
-      tma_load_3d(sQ, &P.tmQK, q_full, h * kHd, q0, b);
-      for (int j = 0; j < nkv; ++j) {
-        const uint32_t ph = j & 1;
-        mbar_wait(k_empty, ph ^ 1);
-        mbar_expect_tx(k_full, 16384);
-        tma_load_3d(sK, &P.tmQK, k_full, P.D + h * kHd, j * kKTile, b);
-        mbar_wait(v_empty, ph ^ 1);
-        mbar_expect_tx(v_full, 16384);
-        tma_load_2d(sV, &P.tmVt, v_full, j * kKTile, (b * P.heads + h) * kHd);
-        tma_load_2d(sV + 8192, &P.tmVt, v_full, j * kKTile + 64, (b * P.heads + h) * kHd);
+      int ks = 0, vs = 0;
+      uint32_t kph = 0, vph = 0, qe_ph = 0;
+      for (int item = blockIdx.x; item < P.n_items; item += gridDim.x) {
+        const int pair = item % P.n_pairs, bh = item / P.n_pairs;
+        const int h = bh % P.heads, b = bh / P.heads;
+        const int q0 = pair * 2 * kQTile;
+        mbar_wait(q_empty, qe_ph ^ 1); qe_ph ^= 1;
+        mbar_expect_tx(q_full, 2 * kTileBytes);
+        tma_load_3d(sQ, &P.tmQK, q_full, h * kHd, q0, b);
+        tma_load_3d(sQ + kTileBytes, &P.tmQK, q_full, h * kHd, q0 + kQTile, b);   // rows >= seq are zero-filled
+        for (int j = 0; j < nkv; ++j) {
+          mbar_wait(&k_empty[ks], kph ^ 1);
+          mbar_expect_tx(&k_full[ks], kTileBytes);
+          tma_load_3d(sK + ks * kTileBytes, &P.tmQK, &k_full[ks], P.D + h * kHd, j * kKTile, b);
+          if (++ks == kKS) { ks = 0; kph ^= 1; }
+          mbar_wait(&v_empty[vs], vph ^ 1);
+          mbar_expect_tx(&v_full[vs], kTileBytes);
+          tma_load_2d(sV + vs * kTileBytes, &P.tmVt, &v_full[vs], j * kKTile, (b * P.heads + h) * kHd);
+          tma_load_2d(sV + vs * kTileBytes + 8192, &P.tmVt, &v_full[vs], j * kKTile + 64, (b * P.heads + h) * kHd);
+          if (++vs == kVS) { vs = 0; vph ^= 1; }
+        }
       }
     }
   } else if (warp == 9) {
+    // ===================== MMA issuer =====================
     if (lane == 0) {
-      const uint32_t idesc_s = umma_idesc_bf16(128, 128);
-      const uint32_t idesc_o = umma_idesc_bf16(128, 64);
-      const uint64_t dq = umma_desc_k128(smem_u32(sQ));
-      const uint64_t dk = umma_desc_k128(smem_u32(sK));
-      const uint64_t dv0 = umma_desc_k128(smem_u32(sV)), dv1 = umma_desc_k128(smem_u32(sV + 8192));
-      const uint64_t dp0 = umma_desc_k128(smem_u32(sP)), dp1 = umma_desc_k128(smem_u32(sP + 16384));
-      mbar_wait(q_full, 0);
-      mbar_wait(k_full, 0);
-      tc_fence_after();
-#pragma unroll
-      for (int k = 0; k < 4; ++k) umma_bf16(tmem_S, dq + 2 * k, dk + 2 * k, idesc_s, k != 0);
-      umma_commit(k_empty);
-      umma_commit(s_full);
-      for (int j = 0; j < nkv; ++j) {
-        const uint32_t ph = j & 1;
-        mbar_wait(p_full, ph);
-        mbar_wait(v_full, ph);
-        mbar_wait(o_empty, ph ^ 1);
+      const uint32_t idesc_o = umma_idesc_bf16(128, kHd);
+      int ks = 0, vs = 0;
+      uint32_t kph = 0, vph = 0, qf_ph = 0;
+      uint32_t sfree_ph[2] = {0, 0}, pfull_ph[2] = {0, 0}, ofree_ph[2] = {0, 0};
+      for (int item = blockIdx.x; item < P.n_items; item += gridDim.x) {
+        const int q0 = (item % P.n_pairs) * 2 * kQTile;
+        const int nt = (q0 + kQTile < seq) ? 2 : 1;            // Q tiles of this item that hold queries
+        mbar_wait(q_full, qf_ph); qf_ph ^= 1;
         tc_fence_after();
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          const uint64_t pa = (k < 4 ? dp0 : dp1) + 2 * (k & 3);
-          const uint64_t vb = (k < 4 ? dv0 : dv1) + 2 * (k & 3);
-          umma_bf16(tmem_O, pa, vb, idesc_o, k != 0);
-        }
-        umma_commit(v_empty);
-        umma_commit(o_full);
-        if (j + 1 < nkv) {
-          mbar_wait(k_full, ph ^ 1);
+        const uint64_t dq0 = umma_desc_k128(smem_u32(sQ));
+        // S_t = Q_t K_j^T for both tiles, one K stage
+        auto issue_qk = [&](int j) {
+          const int kv_len = min(kKTile, seq - j * kKTile);
+          const uint32_t idesc_s = umma_idesc_bf16(128, (kv_len + 15) & ~15);
+          mbar_wait(&k_full[ks], kph);
           tc_fence_after();
+          const uint64_t dk = umma_desc_k128(smem_u32(sK + ks * kTileBytes));
 #pragma unroll
-          for (int k = 0; k < 4; ++k) umma_bf16(tmem_S, dq + 2 * k, dk + 2 * k, idesc_s, k != 0);
-          umma_commit(k_empty);
-          umma_commit(s_full);
+          for (int t = 0; t < 2; ++t) {
+            if (t < nt) {
+              mbar_wait(&s_free[t], sfree_ph[t] ^ 1); sfree_ph[t] ^= 1;
+              tc_fence_after();
+              const uint64_t dq = dq0 + t * (kTileBytes >> 4);
+#pragma unroll
+              for (int k = 0; k < 4; ++k) umma_bf16(tmem_base + kColS + t * 128, dq + 2 * k, dk + 2 * k, idesc_s, k != 0);
+              umma_commit(&s_full[t]);
+            }
+          }
+          umma_commit(&k_empty[ks]);
+          if (++ks == kKS) { ks = 0; kph ^= 1; }
+        };
+        issue_qk(0);
+        for (int j = 0; j < nkv; ++j) {
+          if (j + 1 < nkv) issue_qk(j + 1);                    // overlaps the softmax of block j
+          else umma_commit(q_empty);                           // every QK^T of the item is issued: Q may be replaced
+          const int nk = (min(kKTile, seq - j * kKTile) + 15) >> 4;     // 16-key MMA steps of this block
+          mbar_wait(&v_full[vs], vph);
+          tc_fence_after();
+          const uint64_t dv0 = umma_desc_k128(smem_u32(sV + vs * kTileBytes));
+          const uint64_t dv1 = umma_desc_k128(smem_u32(sV + vs * kTileBytes + 8192));
+#pragma unroll
+          for (int t = 0; t < 2; ++t) {
+            if (t < nt) {
+              mbar_wait(&p_full[t], pfull_ph[t]); pfull_ph[t] ^= 1;
+              if (j == 0) { mbar_wait(&o_free[t], ofree_ph[t] ^ 1); ofree_ph[t] ^= 1; }
+              tc_fence_after();
+              const uint32_t tO = tmem_base + kColO + t * 64, tP = tmem_base + kColP + t * 64;
+              for (int k = 0; k < nk; ++k)
+                umma_bf16_ts(tO, tP + k * 8, (k < 4 ? dv0 : dv1) + 2 * (k & 3), idesc_o, (j | k) != 0);
+              umma_commit(&o_done[t]);
+            }
+          }
+          umma_commit(&v_empty[vs]);
+          if (++vs == kVS) { vs = 0; vph ^= 1; }
         }
       }
     }
   } else {
-    // ===================== softmax / output warps: two threads (one per half) per query row =====================
-    const int q = warp & 3, hh = warp >> 2;
-    const int r = q * 32 + lane;
+    // ===================== softmax warps: one thread per query row =====================
+    const int t = warp >> 2, q = warp & 3;
     const uint32_t lane_sel = static_cast<uint32_t>(q * 32) << 16;
-    const uint32_t s_col = hh * 64;                 // first score column owned by this thread
-    float o_acc[32];
-#pragma unroll
-    for (int i = 0; i < 32; ++i) o_acc[i] = 0.0f;
-    float m_run = -INFINITY, l_run = 0.0f;
-    uint8_t* prow = sP + hh * 16384 + r * 128;      // P sub-tile hh holds key columns [64 hh, 64 hh + 64)
-    for (int j = 0; j < nkv; ++j) {
-      const uint32_t ph = j & 1;
-      const int kvalid = min(kKTile, P.seq - j * kKTile) - static_cast<int>(s_col);   // valid keys among my 64 columns
-      const bool full = kvalid >= 64;
-      mbar_wait(s_full, ph);
-      tc_fence_after();
-      uint32_t v[32];
-      float mr[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
-      // pass 1: partial row max over my 64 columns (chunk A, then chunk B which stays in registers)
-#pragma unroll
-      for (int c2 = 0; c2 < 2; ++c2) {
-        tmem_ld32(tmem_S + lane_sel + s_col + c2 * 32, v);
-        tmem_ld_wait();
-        if (full) {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) mr[i & 3] = fmaxf(mr[i & 3], __uint_as_float(v[i]));
-        } else {
-#pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (c2 * 32 + i < kvalid) mr[i & 3] = fmaxf(mr[i & 3], __uint_as_float(v[i]));
+    const uint32_t tS = tmem_base + lane_sel + kColS + t * 128;
+    const uint32_t tO = tmem_base + lane_sel + kColO + t * 64;
+    const uint32_t tP = tmem_base + lane_sel + kColP + t * 64;
+    const float scale = P.scale_log2;
+    uint32_t sfull_ph = 0, odone_ph = 0;
+    for (int item = blockIdx.x; item < P.n_items; item += gridDim.x) {
+      const int pair = item % P.n_pairs, bh = item / P.n_pairs;
+      const int h = bh % P.heads, b = bh / P.heads;
+      const int row0 = pair * 2 * kQTile + t * kQTile;
+      if (row0 >= seq) continue;                               // this tile holds no queries: no barrier traffic at all
+      const bool warp_active = row0 + q * 32 < seq;            // warp-uniform
+      const int tok = row0 + q * 32 + lane;
+      float m_run = -INFINITY, l_run = 0.0f;
+      for (int j = 0; j < nkv; ++j) {
+        const int kv_len = min(kKTile, seq - j * kKTile);
+        mbar_wait(&s_full[t], sfull_ph); sfull_ph ^= 1;
+        if (!warp_active) {                                    // keep the barrier protocol, skip the math
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&s_free[t]);
+          if (j > 0) { mbar_wait(&o_done[t], odone_ph); odone_ph ^= 1; }
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&p_full[t]);
+          continue;
         }
-      }
-      const float m_part = fmaxf(fmaxf(mr[0], mr[1]), fmaxf(mr[2], mr[3]));
-      float* x = xch + ph * 256;
-      x[hh * 128 + r] = m_part;
-      asm volatile("bar.sync %0, 64;" ::"r"(q + 1) : "memory");
-      const float m_raw = fmaxf(m_part, x[(hh ^ 1) * 128 + r]);
-      const float m_new = fmaxf(m_run, m_raw * P.scale_log2);
-      const float alpha = ex2_approx(m_run - m_new);
-      float ls[4] = {0.f, 0.f, 0.f, 0.f};
-      // pass 2: chunk B is still in v; then chunk A is re-read
+        tc_fence_after();
+        bool waited = false;
+        // O_t *= alpha, issued by the rows' own threads (rare: only when some row's max moved by > 2^8)
+        auto rescale = [&](float m_new) {
+          const float alpha = ex2_approx(m_run - m_new);
+          m_run = m_new;
+          l_run *= alpha;
+          mbar_wait(&o_done[t], odone_ph); odone_ph ^= 1;      // PV of block j-1 must have landed in O
+          waited = true;
+          tc_fence_after();
+#pragma unroll 1
+          for (int part = 0; part < 4; ++part) {               // 16 columns at a time: the 128 scores stay in registers
+            uint32_t o[16];
+            tmem_ld16(tO + part * 16, o);
+            tmem_ld_wait();
 #pragma unroll
-      for (int c2 = 1; c2 >= 0; --c2) {
-        if (c2 == 0) {
-          tmem_ld32(tmem_S + lane_sel + s_col, v);
+            for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+            tmem_st16(tO + part * 16, o);
+          }
+          tmem_st_wait();
+        };
+        if (kv_len == kKTile) {
+          uint32_t s0[32], s1[32], s2[32], s3[32];
+          tmem_ld32(tS, s0); tmem_ld32(tS + 32, s1); tmem_ld32(tS + 64, s2); tmem_ld32(tS + 96, s3);
           tmem_ld_wait();
-        }
-        float p[32];
-        if (full) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&s_free[t]);              // QK^T of block j+1 may overwrite S now
+          float a0 = -INFINITY, a1 = -INFINITY, a2 = -INFINITY, a3 = -INFINITY;
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            p[i] = ex2_approx(fmaf(__uint_as_float(v[i]), P.scale_log2, -m_new));
-            ls[i & 3] += p[i];
+          for (int i = 0; i < 32; i += 2) {
+            a0 = max3(a0, __uint_as_float(s0[i]), __uint_as_float(s0[i + 1]));
+            a1 = max3(a1, __uint_as_float(s1[i]), __uint_as_float(s1[i + 1]));
+            a2 = max3(a2, __uint_as_float(s2[i]), __uint_as_float(s2[i + 1]));
+            a3 = max3(a3, __uint_as_float(s3[i]), __uint_as_float(s3[i + 1]));
           }
+          const float m_new = fmaxf(m_run, fmaxf(fmaxf(a0, a1), fmaxf(a2, a3)) * scale);
+          if (j == 0) m_run = m_new;
+          else if (__any_sync(0xffffffffu, m_new - m_run > kRescaleThreshold)) rescale(m_new);
+          const uint64_t sc2 = pack2f(scale, scale), nm2 = pack2f(-m_run, -m_run);
+          uint64_t sum_a = 0, sum_b = 0;                       // bit pattern of (+0.0f, +0.0f)
+          uint32_t pk[16];
+          softmax_chunk(s0, sc2, nm2, sum_a, sum_b, pk);
+          if (j > 0 && !waited) {                              // PV of block j-1 has consumed the previous P
+            mbar_wait(&o_done[t], odone_ph); odone_ph ^= 1;
+            tc_fence_after();
+          }
+          tmem_st16(tP, pk);
+          softmax_chunk(s1, sc2, nm2, sum_a, sum_b, pk);
+          tmem_st16(tP + 16, pk);
+          softmax_chunk(s2, sc2, nm2, sum_a, sum_b, pk);
+          tmem_st16(tP + 32, pk);
+          softmax_chunk(s3, sc2, nm2, sum_a, sum_b, pk);
+          tmem_st16(tP + 48, pk);
+          float x0, x1, y0, y1;
+          unpack2f(sum_a, x0, x1);
+          unpack2f(sum_b, y0, y1);
+          l_run += (x0 + x1) + (y0 + y1);
         } else {
+          // ragged last block: only the chunks that hold keys, masked; two passes over TMEM (cheap: <= 1/8 of the row)
+          const int nch = (kv_len + 31) >> 5;
+          uint32_t v[32];
+          float mx = -INFINITY;
+          for (int c = 0; c < nch; ++c) {
+            tmem_ld32(tS + c * 32, v);
+            tmem_ld_wait();
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            float e = ex2_approx(fmaf(__uint_as_float(v[i]), P.scale_log2, -m_new));
-            p[i] = (c2 * 32 + i < kvalid) ? e : 0.0f;
-            ls[i & 3] += p[i];
+            for (int i = 0; i < 32; ++i)
+              if (c * 32 + i < kv_len) mx = fmaxf(mx, __uint_as_float(v[i]));
+          }
+          const float m_new = fmaxf(m_run, mx * scale);
+          if (j == 0) m_run = m_new;
+          else if (__any_sync(0xffffffffu, m_new - m_run > kRescaleThreshold)) rescale(m_new);
+          float ls = 0.0f;
+          for (int c = 0; c < nch; ++c) {
+            tmem_ld32(tS + c * 32, v);
+            tmem_ld_wait();
+            uint32_t pk[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const float e0 = (c * 32 + 2 * i < kv_len) ? ex2_approx(fmaf(__uint_as_float(v[2 * i]), scale, -m_run)) : 0.0f;
+              const float e1 = (c * 32 + 2 * i + 1 < kv_len) ? ex2_approx(fmaf(__uint_as_float(v[2 * i + 1]), scale, -m_run)) : 0.0f;
+              ls += e0 + e1;
+              pk[i] = pack_bf16(e0, e1);
+            }
+            if (c == 0 && j > 0 && !waited) {
+              mbar_wait(&o_done[t], odone_ph); odone_ph ^= 1;
+              tc_fence_after();
+            }
+            tmem_st16(tP + c * 16, pk);
+          }
+          l_run += ls;
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&s_free[t]);
+        }
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&p_full[t]);
+      }
+      // ---- item epilogue: O / l -> bf16 -> global
+      mbar_wait(&o_done[t], odone_ph); odone_ph ^= 1;
+      if (warp_active) {
+        tc_fence_after();
+        uint32_t o0[32], o1[32];
+        tmem_ld32(tO, o0);
+        tmem_ld32(tO + 32, o1);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&o_free[t]);                // PV of the next item may overwrite O
+        if (tok < seq) {
+          const float inv = 1.0f / l_run;
+          __nv_bfloat16* op = P.out + (static_cast<long long>(b) * seq + tok) * P.out_ld + h * kHd;
+#pragma unroll
+          for (int i = 0; i < 32; i += 8) {
+            *reinterpret_cast<uint4*>(op + i) = make_uint4(
+                pack_bf16(__uint_as_float(o0[i]) * inv, __uint_as_float(o0[i + 1]) * inv),
+                pack_bf16(__uint_as_float(o0[i + 2]) * inv, __uint_as_float(o0[i + 3]) * inv),
+                pack_bf16(__uint_as_float(o0[i + 4]) * inv, __uint_as_float(o0[i + 5]) * inv),
+                pack_bf16(__uint_as_float(o0[i + 6]) * inv, __uint_as_float(o0[i + 7]) * inv));
+            *reinterpret_cast<uint4*>(op + 32 + i) = make_uint4(
+                pack_bf16(__uint_as_float(o1[i]) * inv, __uint_as_float(o1[i + 1]) * inv),
+                pack_bf16(__uint_as_float(o1[i + 2]) * inv, __uint_as_float(o1[i + 3]) * inv),
+                pack_bf16(__uint_as_float(o1[i + 4]) * inv, __uint_as_float(o1[i + 5]) * inv),
+                pack_bf16(__uint_as_float(o1[i + 6]) * inv, __uint_as_float(o1[i + 7]) * inv));
           }
         }
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          const int chunk = c2 * 4 + g;                            // 16-byte chunk index inside the 128-B row
-          uint4 pk = make_uint4(pack_bf16(p[g * 8 + 0], p[g * 8 + 1]), pack_bf16(p[g * 8 + 2], p[g * 8 + 3]),
-                                pack_bf16(p[g * 8 + 4], p[g * 8 + 5]), pack_bf16(p[g * 8 + 6], p[g * 8 + 7]));
-          *reinterpret_cast<uint4*>(prow + ((chunk ^ (r & 7)) << 4)) = pk;
-        }
-      }
-      l_run = l_run * alpha + ((ls[0] + ls[1]) + (ls[2] + ls[3]));
-      m_run = m_new;
-      fence_proxy_async_smem();
-      tc_fence_before();
-      mbar_arrive(p_full);
-      mbar_wait(o_full, ph);
-      tc_fence_after();
-      tmem_ld32(tmem_O + lane_sel + hh * 32, v);
-      tmem_ld_wait();
-#pragma unroll
-      for (int i = 0; i < 32; ++i) o_acc[i] = fmaf(o_acc[i], alpha, __uint_as_float(v[i]));
-      tc_fence_before();
-      mbar_arrive(o_empty);
-    }
-    // combine the two halves' row sums (both used the same running maximum)
-    float* x = xch + 512;
-    x[hh * 128 + r] = l_run;
-    asm volatile("bar.sync %0, 64;" ::"r"(q + 1) : "memory");
-    const float l_tot = l_run + x[(hh ^ 1) * 128 + r];
-    const int tok = q0 + r;
-    if (tok < P.seq) {
-      const float inv = 1.0f / l_tot;
-      __nv_bfloat16* op = P.out + (static_cast<long long>(b) * P.seq + tok) * P.out_ld + h * kHd + hh * 32;
-#pragma unroll
-      for (int i = 0; i < 32; i += 8) {
-        uint4 pk = make_uint4(pack_bf16(o_acc[i] * inv, o_acc[i + 1] * inv), pack_bf16(o_acc[i + 2] * inv, o_acc[i + 3] * inv),
-                              pack_bf16(o_acc[i + 4] * inv, o_acc[i + 5] * inv), pack_bf16(o_acc[i + 6] * inv, o_acc[i + 7] * inv));
-        *reinterpret_cast<uint4*>(op + i) = pk;
+      } else {
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&o_free[t]);
       }
     }
   }
@@ -451,7 +391,7 @@ __global__ void __launch_bounds__(kAttn2Threads, 2) pf_attention_kernel_v2(const
   __syncthreads();
   if (warp == 9) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 256);
+    tmem_dealloc(tmem_base, 512);
   }
 }
 
@@ -461,29 +401,30 @@ using namespace pf;
 
 extern "C" int pf_attention(const void* qk, int32_t qk_ld, const void* vt, int32_t B, int32_t seq, int32_t seq_pad,
                             int32_t heads, float scale, void* out, int32_t out_ld, void* stream) {
-  static bool attr_done_dev[kMaxDevices] = {false};
-  bool& attr_done = attr_done_dev[current_device()];
-  static const bool use_v1 = getenv("PF_B200_ATTN_V1") != nullptr;
-  const int smem_bytes = 1024 + 81920 + 128 + 3072;
-  if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(pf_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
-    if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(pf_attention_kernel_v2, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+  static bool attr_done[kMaxDevices] = {false};
+  static int sm_count[kMaxDevices] = {0};
+  const int dev = current_device();
+  if (!attr_done[dev]) {
+    cudaError_t e = cudaFuncSetAttribute(pf_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem);
     if (e != cudaSuccess) return set_error("cudaFuncSetAttribute(pf_attention_kernel): %s", cudaGetErrorString(e));
-    attr_done = true;
+    cudaDeviceGetAttribute(&sm_count[dev], cudaDevAttrMultiProcessorCount, dev);
+    attr_done[dev] = true;
   }
   const int D = heads * kHd;
+  if (B < 1 || seq < 1 || heads < 1) return set_error("pf_attention: empty problem");
   if (qk_ld % 8 || seq_pad % 8 || out_ld % 8) return set_error("pf_attention: strides must be multiples of 8");
+  if (seq_pad < seq) return set_error("pf_attention: seq_pad %d < seq %d", seq_pad, seq);
   AttnParams P;
   if (tmap_3d_bf16(&P.tmQK, qk, 2 * D, seq, B, qk_ld, static_cast<uint64_t>(seq) * qk_ld, 64, 128, 1)) return 1;
   if (tmap_2d_bf16(&P.tmVt, vt, seq_pad, static_cast<uint64_t>(B) * heads * kHd, seq_pad, 64, 64)) return 1;
   P.B = B; P.seq = seq; P.heads = heads; P.D = D;
+  P.n_pairs = (seq + 2 * kQTile - 1) / (2 * kQTile);
+  P.n_items = B * heads * P.n_pairs;
   P.scale_log2 = scale * 1.4426950408889634f;
   P.out = static_cast<__nv_bfloat16*>(out);
   P.out_ld = out_ld;
-  dim3 grid((seq + kQTile - 1) / kQTile, heads, B);
-  cudaError_t le = use_v1 ? launch_pdl(pf_attention_kernel, grid, dim3(kAttnThreads), smem_bytes, static_cast<cudaStream_t>(stream), P)
-                          : launch_pdl(pf_attention_kernel_v2, grid, dim3(kAttn2Threads), smem_bytes, static_cast<cudaStream_t>(stream), P);
+  const int grid = P.n_items < sm_count[dev] ? P.n_items : sm_count[dev];
+  cudaError_t le = launch_pdl(pf_attention_kernel, dim3(grid), dim3(kAttnThreads), kAttnSmem, static_cast<cudaStream_t>(stream), P);
   if (le != cudaSuccess) return set_error("pf_attention_kernel launch: %s", cudaGetErrorString(le));
   return check_launch("pf_attention_kernel");
 }

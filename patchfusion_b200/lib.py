@@ -121,6 +121,8 @@ class Profiler:
         self.records = []
         self.next_flops = 0.0
         self.next_family = None
+        self.next_label = None
+        self.labels = []
 
     def summary(self):
         torch.cuda.synchronize()
@@ -141,10 +143,12 @@ def call(name, *args):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         fl, PROFILER.next_flops = PROFILER.next_flops, 0.0
         fam, PROFILER.next_family = PROFILER.next_family or name, None
+        lab, PROFILER.next_label = PROFILER.next_label or name, None
         e0.record()
         _call(name, *args)
         e1.record()
         PROFILER.records.append((fam, fl, e0, e1))
+        PROFILER.labels.append(lab)
     else:
         _call(name, *args)
 
