@@ -143,6 +143,24 @@ int pf_ingest_u8(const uint8_t* img_hwc, int32_t H, int32_t W, int32_t bgr, int3
 int pf_depth_to_u16(const float* depth, int32_t H, int32_t W, int32_t OH, int32_t OW, float scale, uint16_t* out,
                     void* stream);
 
+/* compute_metrics / compute_errors / soft_edge_error (estimator/utils/metric.py:10-50, 67-72, 97-148) as one fused
+ * reduction over the ground-truth grid.  pred [PH,PW] fp32 is resampled (bilinear, align_corners=False, metric.py:101-104)
+ * when its shape differs from gt [H,W]; clamped to [min_eval, max_eval] (inf -> max, nan -> min); valid pixels are
+ * min_eval < gt < max_eval (and extra_mask != 0 when given).  edges (nullable, uint8 [H,W]): boundary mask for the
+ * soft edge error.  partials: workspace of nblocks * 12 doubles (device); out: 12 doubles (device), summed in a fixed
+ * order: {n, #thresh<1.25, #<1.25^2, #<1.25^3, sum|gt-p|/gt, sum(gt-p)^2/gt, sum(gt-p)^2, sum(ln gt - ln p)^2,
+ * sum(ln p - ln gt), sum|log10 gt - log10 p|, n_edge, sum see}.  patchfusion_b200/metrics.py turns them into the
+ * reference's dict (a1,a2,a3,abs_rel,rmse,log_10,rmse_log,silog,sq_rel,see). */
+int pf_depth_metrics(const float* pred, int32_t PH, int32_t PW, const float* gt, int32_t H, int32_t W, float min_eval,
+                     float max_eval, const uint8_t* edges, const uint8_t* extra_mask, double* partials, int32_t nblocks,
+                     double* out, void* stream);
+/* colorize (estimator/utils/color.py:95-140) after the percentile normalisation: x = (d - vmin)/(vmax - vmin),
+ * LUT index int(x*256) clipped to [0,255] (matplotlib Colormap.__call__(bytes=True)), d == invalid_val or NaN ->
+ * background (128,128,128); lut_rgb: 256 x 3 uint8 (device); out [n,3] uint8, channel order BGR when bgr != 0
+ * (tester.py:67-69 writes `[:, :, [2,1,0]]` through cv2). */
+int pf_colorize_u8(const float* depth, int64_t n, float vmin, float vmax, float invalid_val, const uint8_t* lut_rgb,
+                   int32_t bgr, uint8_t* out, void* stream);
+
 /* ---- Swin / G2L (estimator/models/blocks/swin_layers.py) ------------------------------------------------------ */
 /* x[h*w, C] fp32 = NHWC bf16 feature + absolute_pos_embed (swin_layers.py:419-422) */
 int pf_g2l_embed(const void* feat, int32_t feat_ld, const float* ape, int32_t n, int32_t C, float* x, void* stream);

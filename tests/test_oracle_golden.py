@@ -59,3 +59,17 @@ def test_infer_m1_against_reference(ctx):
     want = g['infer_m1']
     assert y[..., ::st, ::st].shape == want.shape
     assert np.abs(y[..., ::st, ::st].numpy() - want).max() < 1e-3 * np.abs(want).max()
+
+
+def test_metrics_oracle_matches_reference_fixture():
+    """oracle/metrics_oracle.py (numpy restatement of estimator/utils/metric.py) against the values the real reference
+    produced in the build container (oracle/make_golden_metrics.py)."""
+    import json
+    from oracle import metrics_oracle as mo
+    from oracle.make_golden_metrics import case_tensors
+    for ent in json.load(open(os.path.join(GOLD, 'metrics_case0.json'))):
+        c = ent['case']
+        gt, pred, edges = case_tensors(c)
+        got = mo.compute_metrics(gt, pred, c['lo'], c['hi'], edges)
+        for k, v in ent['reference'].items():
+            assert abs(float(got[k]) - v) <= 1e-6 * max(1.0, abs(v)), (c['name'], k)

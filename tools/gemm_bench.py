@@ -25,13 +25,39 @@ SHAPES = [
     ('inc 3x3 8->32 @392x518 x7', 'conv', (7, 392, 518, [8], 32)),
     ('1x1 256->256 @112x148 x7', 'conv1', (7, 112, 148, [256], 256)),
     ('clb0 1x1 [32,128]->80 @392x518 x7', 'conv1', (7, 392, 518, [32, 128], 80)),
+    ('clbT 1x1 [32,128]->80 gelu + tail 80->4 softplus @392x518 x9', 'conv1t', (9, 392, 518, [32, 128], 80)),
+    ('vit proj   M9333 K1024 N1024 gamma', 'ling', (9333, 1024, 1024)),
+    ('vit fc1    M9333 K1024 N4096 gelu', 'linact', (9333, 1024, 4096)),
 ]
 only = sys.argv[1:] 
 res = []
 for name, kind, p in SHAPES:
     if only and not any(o in name for o in only):
         continue
-    if kind == 'lin':
+    if kind in ('ling', 'linact'):
+        M, K, N = p
+        x = torch.randn(M, K, device=dev).to(torch.bfloat16)
+        w = torch.randn(N, K, device=dev) / K ** 0.5
+        pw = ops.pack_weight(w, torch.randn(N, device=dev))
+        if kind == 'ling':
+            out = torch.zeros(M, N, dtype=torch.float32, device=dev)
+            gam = torch.rand(N, device=dev)
+            fn = lambda: ops.gemm(pw, [x], out, gamma=gam)
+        else:
+            out = torch.empty(M, N, dtype=torch.bfloat16, device=dev)
+            fn = lambda: ops.gemm(pw, [x], out, act=ops.ACT_GELU)
+        flops = 2.0 * M * K * N
+    elif kind == 'conv1t':
+        NB, H, W, cs, N = p
+        srcs = [torch.randn(NB, H, W, c, device=dev).to(torch.bfloat16) for c in cs]
+        w = torch.randn(N, sum(cs), 1, 1, device=dev) / sum(cs) ** 0.5
+        pw = ops.pack_weight(w, torch.randn(N, device=dev), src_c=cs)
+        w2, b2 = torch.randn(4, N, device=dev) / N ** 0.5, torch.randn(4, device=dev)
+        out = torch.empty(NB, H, W, ops.pad_to(N, 8), dtype=torch.bfloat16, device=dev)
+        pt = torch.empty(NB, H, W, 8, dtype=torch.float32, device=dev)
+        fn = lambda: ops.gemm(pw, srcs, out, image=(NB, H, W), act=ops.ACT_GELU, tail=(w2, b2, ops.ACT_SOFTPLUS), tail_out=pt, skip_main=True)
+        flops = 2.0 * NB * H * W * sum(cs) * N
+    elif kind == 'lin':
         M, K, N = p
         x = torch.randn(M, K, device=dev).to(torch.bfloat16)
         w = torch.randn(N, K, device=dev) / K ** 0.5
