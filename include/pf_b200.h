@@ -16,6 +16,7 @@
 #ifndef PF_B200_H_
 #define PF_B200_H_
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -32,6 +33,12 @@ const char* pf_last_error(void);
 int pf_version(void);
 /* number of kernels launched by this library since process start (bench.py's gpu_launches) */
 long long pf_launch_count(void);
+/* Per-launch profiler: between start and stop every kernel this library launches on `stream` is bracketed by CUDA
+ * events (duration i = event i - event i-1).  pf_profile_stop returns the record count; pf_profile_get returns a
+ * record's kernel name, shape label, algorithmic flops (0 for HBM kernels) and milliseconds. */
+int pf_profile_start(void* stream);
+int pf_profile_stop(void);
+int pf_profile_get(int32_t i, const char** name, const char** label, double* flops, float* ms);
 
 /* ---- dense contractions: one tcgen05/TMEM/TMA implicit-GEMM kernel ---------------------------------------------
  * Replaces every nn.Linear / nn.Conv2d(1x1, 3x3 s1 p1) / nn.ConvTranspose2d(k==s) on the path:
@@ -213,6 +220,126 @@ int pf_stitch_reduce(float* stack, int32_t world, int64_t n, void* stream);
 /* RunningAverageMap.resize (utils.py:32-36): num' = nearest(avg) * bilinear_ac(cnt), den' = bilinear_ac(cnt) */
 int pf_stitch_resize(const float* num, const float* den, int32_t H, int32_t W, int32_t OH, int32_t OW, float* num_out,
                      float* den_out, void* stream);
+
+
+/* ================================================================================================================
+ * STAGE-LEVEL ENTRY POINTS: the kernel sequences behind the reference's methods, issued by the
+ * library itself from caller-owned weights and ONE caller-owned workspace per call (no allocation inside; every
+ * intermediate is bump-allocated from the workspace in a fixed order, so addresses are a function of (weights, batch)
+ * only: TMA tensor maps are cached and the whole call is CUDA-graph capturable).
+ *
+ *   pf_branch_forward   PatchFusion.coarse_forward / fine_forward  (estimator/models/patchfusion.py:189-225) =
+ *                       ZoeDepth.forward (zoedepth_v1.py:125-233) over DepthAnythingCore (depth_anything.py:262-278),
+ *                       DPT_DINOv2 (dpt.py:97-157) and DinoVisionTransformer.get_intermediate_layers
+ *                       (vision_transformer.py:297-321)
+ *   pf_g2l_forward      G2LFusion.forward on the six whole-image coarse maps (swin_layers.py:410-432), once per image
+ *   pf_fusion_forward   PatchFusion.fusion_forward (patchfusion.py:259-340) incl. coarse_postprocess_test's ROI
+ *                       crop-zoom (:240-257) and GuidedFusionPatchFusion.forward (guided_fusion_model.py:163-207)
+ * ================================================================================================================ */
+
+/* one packed dense layer: the panel written by pf_pack_weight / pf_pack_weight_convT + its fp32 bias */
+typedef struct pf_layer {
+  const void* w;            /* bf16 [N_pad, Ktot] K-major */
+  const float* bias;        /* [N] or NULL */
+  int32_t N, Ktot, taps;    /* taps: 1 or 9 */
+  int32_t num_src;          /* concat sources the panel was packed for */
+  int32_t src_c[3];         /* logical channels of each */
+  int32_t ps, ps_cout;      /* ConvTranspose k == stride: k and Cout (else 0) */
+  const float* w2;          /* optional trailing 1x1 layer fused into the epilogue: fp32 [n2, N] */
+  const float* b2;          /* [n2] or NULL */
+  int32_t n2;
+} pf_layer;
+
+typedef struct pf_vit_block {             /* dinov2/layers/block.py:82-107 */
+  const float* n1w; const float* n1b; const float* n2w; const float* n2b;
+  const float* ls1; const float* ls2;     /* LayerScale gammas */
+  pf_layer qkv, proj, fc1, fc2;
+} pf_vit_block;
+
+typedef struct pf_head {                  /* metric-bins head: zoedepth_v1.py:173-219 / patchfusion.py:297-339 */
+  pf_layer seed0, seed2;                  /* seed_bin_regressor._net.{0,2} */
+  pf_layer seedproj0, seedproj2;          /* seed_projector */
+  pf_layer proj0[4], proj2[4];            /* projectors.N */
+  pf_layer att0[4], att2[4];              /* attractors.N (att0 carries the fused N<=16 second layer) */
+  pf_layer clb0;                          /* conditional_log_binomial.mlp.0 (+ fused mlp.2) */
+  int32_t n_attractors[4];
+  int32_t n_bins, bin_embedding_dim;
+  int32_t attractor_flags;                /* PF_ATTRACTOR_MEAN | PF_ATTRACTOR_EXP */
+  int32_t has_rel;                        /* CLB input carries the relative-depth channel (branch heads) */
+  float min_temp, max_temp;
+} pf_head;
+
+typedef struct pf_branch {                /* one ZoeDepth(Depth-Anything) branch */
+  int32_t H, W;                           /* patch_process_shape (multiples of 14) */
+  int32_t dim, depth, heads, features;
+  int32_t out_channels[4];
+  pf_layer patch;                         /* patch_embed.proj as a K=592 GEMM */
+  const float* pos;                       /* [1 + gh*gw, dim] pos_embed already resampled (vision_transformer.py:189-210) */
+  const float* cls;                       /* [dim] */
+  const pf_vit_block* blocks;             /* host array [depth] */
+  const float* nw; const float* nb;       /* final norm */
+  pf_layer proj[4];                       /* depth_head.projects */
+  pf_layer rs0, rs1, rs3;                 /* resize_layers 0,1 (ConvTranspose), 3 (3x3 s2 as GEMM over pf_im2col_3x3_s2) */
+  pf_layer rn[4];                         /* scratch.layerN_rn */
+  pf_layer ff_out[4];                     /* refinenet{1..4}.out_conv (index = N-1) */
+  pf_layer ff_c1[4][2], ff_c2[4][2];      /* refinenetN.resConfUnit{1,2}.conv{1,2} */
+  pf_layer oc1, oc2;                      /* output_conv1, output_conv2.0 (+ fused output_conv2.2) */
+  pf_layer conv2;
+  pf_head head;
+} pf_branch;
+
+typedef struct pf_g2l_block {             /* SwinTransformerBlock, swin_layers.py:218-268 */
+  const float* n1w; const float* n1b; const float* n2w; const float* n2b;
+  const float* table;                     /* relative_position_bias_table [529, heads] */
+  pf_layer qkv, proj, fc1, fc2;
+} pf_g2l_block;
+
+typedef struct pf_g2l_level {
+  int32_t C, heads, depth;
+  const float* ape;                       /* absolute_pos_embed [h*w, C] */
+  int32_t ape_rows;
+  const float* nw; const float* nb;       /* g2l_layer_norm */
+  const float* ones;                      /* [C] of 1.0 (plain residual through the LayerScale epilogue) */
+  const pf_g2l_block* blocks;             /* host array [depth] */
+} pf_g2l_level;
+
+typedef struct pf_fusion {
+  int32_t H, W;                           /* patch_process_shape */
+  pf_layer fc[5];                         /* fusion_conv_list.0..4 */
+  pf_layer inc[2];                        /* guided_fusion.inc (BatchNorm folded) */
+  pf_layer down[5][2];
+  pf_layer up[5][2];                      /* up_conv_list.N.conv.double_conv.{0,2} */
+  pf_layer cv[6][2];                      /* convs.N */
+  pf_g2l_level g2l[6];                    /* low -> high resolution */
+  pf_head head;
+} pf_fusion;
+
+typedef struct pf_map { void* ptr; int32_t B, H, W, C, ld; } pf_map;     /* NHWC bf16 activation */
+typedef struct pf_branch_out { float* depth; pf_map feats[6]; } pf_branch_out;   /* x_d0, r4, r3, r2, r1, out_conv */
+
+/* debug tap: called (synchronously, while enqueuing) after the named intermediate has been produced */
+typedef void (*pf_tap_fn)(void* user, const char* name, const void* ptr, int32_t is_f32, int64_t rows, int32_t cols,
+                          int32_t ld);
+
+size_t pf_branch_workspace_bytes(const pf_branch* w, int32_t B);
+/* images: planar fp32 [B,3,H,W] in [0,1], un-normalised.  out->depth [B,H,W] fp32 and the six taps live inside ws. */
+int pf_branch_forward(const pf_branch* w, const float* images, int32_t B, void* ws, size_t ws_bytes, pf_branch_out* out,
+                      pf_tap_fn tap, void* tap_user, void* stream);
+size_t pf_g2l_workspace_bytes(const pf_fusion* w, const pf_map* coarse_feats);
+int pf_g2l_forward(const pf_fusion* w, const pf_map* coarse_feats, void* ws, size_t ws_bytes, pf_map* out,
+                   void* stream);
+size_t pf_fusion_workspace_bytes(const pf_fusion* w, int32_t T, const pf_map* g2l_maps);
+/* crops planar fp32 [T,3,H,W]; boxes fp32 [T,4] (x1,y1,x2,y2 in patch_process units, device); fine_* = the fine
+ * branch's outputs for the same T tiles; coarse_* / g2l_maps = the whole-image (batch 1) outputs; depth_out [T,H,W]. */
+int pf_fusion_forward(const pf_fusion* w, const float* crops, const float* boxes, int32_t T, const float* fine_depth,
+                      const pf_map* fine_feats, const float* coarse_depth, const pf_map* coarse_feats,
+                      const pf_map* g2l_maps, void* ws, size_t ws_bytes, float* depth_out, pf_tap_fn tap,
+                      void* tap_user, void* stream);
+/* LayerNorm of rows [skip, skip + rows_out) of each group of rows_in rows (the patch tokens of every image, cls
+ * dropped: vision_transformer.py:309-312): out row g*rows_out + i <- x row g*rows_in + skip + i */
+int pf_layernorm_grouped(const float* x, int32_t x_ld, const float* w, const float* b, float eps, int32_t groups,
+                         int32_t rows_in, int32_t skip, int32_t rows_out, int32_t C, void* out, int32_t out_ld,
+                         void* stream);
 
 #ifdef __cplusplus
 }

@@ -5,8 +5,9 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
-SOURCES = ['pf_api.cu', 'pf_gemm.cu', 'pf_attn.cu', 'pf_elem.cu', 'pf_post.cu']
-LIB = os.path.join(HERE, 'libpf_b200.so')
+SOURCES = ['pf_api.cu', 'pf_gemm.cu', 'pf_attn.cu', 'pf_elem.cu', 'pf_post.cu', 'pf_stage.cu']
+LIB = os.path.join(HERE, os.environ.get('PF_B200_LIBNAME', 'libpf_b200.so'))
+EXTRA = os.environ.get('PF_B200_NVCC_EXTRA', '').split()
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
               '-Xcompiler', '-fPIC']
 
@@ -27,8 +28,8 @@ def build(force=False, verbose=False):
     os.makedirs(os.path.join(HERE, 'build'), exist_ok=True)
     procs = []
     for src in SOURCES:
-        obj = os.path.join(HERE, 'build', src.replace('.cu', '.o'))
-        cmd = [nvcc] + NVCC_FLAGS + (['-Xptxas', '-v'] if verbose else []) + ['-c', os.path.join(CSRC, src), '-o', obj]
+        obj = os.path.join(HERE, 'build', os.path.basename(LIB) + '.' + src.replace('.cu', '.o'))
+        cmd = [nvcc] + NVCC_FLAGS + EXTRA + (['-Xptxas', '-v'] if verbose else []) + ['-c', os.path.join(CSRC, src), '-o', obj]
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
         objs.append(obj)
     for src, p in procs:

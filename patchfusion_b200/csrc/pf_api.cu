@@ -8,6 +8,7 @@
 #include <atomic>
 #include <mutex>
 #include <unordered_map>
+#include <vector>
 
 #include "pf_kernels.h"
 
@@ -23,7 +24,36 @@ int set_error(const char* fmt, ...) {
   va_end(ap);
   return 1;
 }
-void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+// ---- per-launch profiler (bench.py's roofline pass): one CUDA event after every launch of this library on the
+// profiled stream; the duration of launch i is event[i] - event[i-1] (launches are back to back on one stream).
+struct ProfRec { const char* name; double flops; char label[80]; cudaEvent_t ev; };
+static std::vector<ProfRec> g_prof;
+static bool g_prof_on = false;
+static cudaStream_t g_prof_stream = nullptr;
+static cudaEvent_t g_prof_ev0 = nullptr;
+static thread_local double g_next_flops = 0.0;
+static thread_local char g_next_label[80] = "";
+
+void note_work(double flops, const char* fmt, ...) {
+  if (!g_prof_on) return;
+  g_next_flops = flops;
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_next_label, sizeof(g_next_label), fmt, ap);
+  va_end(ap);
+}
+void count_launch(const char* name) {
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  if (g_prof_on) {
+    ProfRec r;
+    r.name = name; r.flops = g_next_flops;
+    snprintf(r.label, sizeof(r.label), "%s", g_next_label[0] ? g_next_label : name);
+    cudaEventCreate(&r.ev);
+    cudaEventRecord(r.ev, g_prof_stream);
+    g_prof.push_back(r);
+    g_next_flops = 0.0; g_next_label[0] = 0;
+  }
+}
 bool pdl_enabled() {
   // opt-in (PF_B200_PDL=1): measured neutral inside CUDA graphs on B200, so the default stays the plain launch
   static const bool on = getenv("PF_B200_PDL") != nullptr && getenv("PF_B200_PDL")[0] == '1';
@@ -32,7 +62,7 @@ bool pdl_enabled() {
 int check_launch(const char* what) {
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_error("%s launch: %s", what, cudaGetErrorString(e));
-  count_launch();
+  count_launch(what);
   return 0;
 }
 
@@ -187,6 +217,30 @@ const char* pf_last_error(void) { return g_err; }
 int pf_version(void) { return 100; }
 long long pf_launch_count(void) { return g_launches.load(); }
 
+int pf_profile_start(void* stream) {
+  for (auto& r : g_prof) cudaEventDestroy(r.ev);
+  g_prof.clear();
+  if (g_prof_ev0) cudaEventDestroy(g_prof_ev0);
+  g_prof_stream = static_cast<cudaStream_t>(stream);
+  cudaEventCreate(&g_prof_ev0);
+  cudaEventRecord(g_prof_ev0, g_prof_stream);
+  g_prof_on = true;
+  return 0;
+}
+int pf_profile_stop(void) {
+  g_prof_on = false;
+  if (!g_prof.empty()) cudaEventSynchronize(g_prof.back().ev);
+  return static_cast<int>(g_prof.size());
+}
+int pf_profile_get(int32_t i, const char** name, const char** label, double* flops, float* ms) {
+  if (i < 0 || i >= static_cast<int>(g_prof.size())) return set_error("pf_profile_get: index %d out of range", i);
+  const ProfRec& r = g_prof[i];
+  *name = r.name; *label = r.label; *flops = r.flops;
+  cudaError_t e = cudaEventElapsedTime(ms, i == 0 ? g_prof_ev0 : g_prof[i - 1].ev, r.ev);
+  if (e != cudaSuccess) return set_error("cudaEventElapsedTime: %s", cudaGetErrorString(e));
+  return 0;
+}
+
 int pf_pack_weight(const float* w, int32_t N, int32_t N_pad, int32_t num_src, const int32_t* src_c, int32_t taps,
                    const float* scale, void* dst, void* stream) {
   if (num_src < 1 || num_src > 3 || (taps != 1 && taps != 9)) return set_error("pf_pack_weight: bad arguments");
@@ -234,6 +288,7 @@ int pf_gemm(pf_gemm_desc* u, void* stream) {
   int ksteps = 0;
   for (int s = 0; s < u->num_src; ++s) {
     d.chunks[s] = (u->a_c[s] + 63) / 64;
+    d.k_true[s] = u->a_c[s];
     u->chunks[s] = d.chunks[s];
     ksteps += d.chunks[s] * u->taps;
     if (u->a_c[s] % 8 || u->a_ld[s] % 8) return set_error("pf_gemm: source %d channels/ld must be multiples of 8", s);

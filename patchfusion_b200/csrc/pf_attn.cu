@@ -14,7 +14,7 @@
 // (Cody-Waite + cubic, packed FFMA2) for the rest - at head_dim 64 the MUFU pipe, not the tensor pipe, bounds
 // attention - packed FADD2 row sums, bf16 P back into TMEM.  O stays in TMEM across KV blocks; it is rescaled (by
 // the row's own thread) only when the running max moves by more than 2^8 (lazy rescale with a stale max, exact after
-// the final 1/l normalisation).  Warp 8 = TMA producer, warp 9 = single-thread MMA issuer.  K_j / V_j are shared by
+// the final 1/l normalisation).  Warp 8 = TMA producer, warps 9 / 10 = single-thread QK^T / PV issuers.  K_j / V_j are shared by
 // the two Q tiles.  The last KV block (1037 = 8*128 + 13 keys) runs with N = 16 / K = 16 instead of a padded 128.
 #include <stdlib.h>
 
@@ -24,7 +24,7 @@
 namespace pf {
 
 constexpr int kQTile = 128, kKTile = 128, kHd = 64;
-constexpr int kAttnThreads = 320;
+constexpr int kAttnThreads = 352;                   // 8 softmax warps + TMA + QK^T issuer + PV issuer
 constexpr int kKS = 3, kVS = 3;                      // K / V smem ring depths
 constexpr int kTileBytes = 16384;
 constexpr int kOffQ = 0;                             // 2 x [128 q][64]
@@ -165,20 +165,19 @@ __global__ void __launch_bounds__(kAttnThreads, 1) pf_attention_kernel(const __g
       }
     }
   } else if (warp == 9) {
-    // ===================== MMA issuer =====================
+    // ===================== QK^T issuer: S_t = Q_t K_j^T as soon as the softmax warps have taken S_t =====================
+    // (a separate thread from the PV issuer, so a QK^T is never queued behind a wait for P)
     if (lane == 0) {
-      const uint32_t idesc_o = umma_idesc_bf16(128, kHd);
-      int ks = 0, vs = 0;
-      uint32_t kph = 0, vph = 0, qf_ph = 0;
-      uint32_t sfree_ph[2] = {0, 0}, pfull_ph[2] = {0, 0}, ofree_ph[2] = {0, 0};
+      int ks = 0;
+      uint32_t kph = 0, qf_ph = 0;
+      uint32_t sfree_ph[2] = {0, 0};
       for (int item = blockIdx.x; item < P.n_items; item += gridDim.x) {
         const int q0 = (item % P.n_pairs) * 2 * kQTile;
         const int nt = (q0 + kQTile < seq) ? 2 : 1;            // Q tiles of this item that hold queries
         mbar_wait(q_full, qf_ph); qf_ph ^= 1;
         tc_fence_after();
         const uint64_t dq0 = umma_desc_k128(smem_u32(sQ));
-        // S_t = Q_t K_j^T for both tiles, one K stage
-        auto issue_qk = [&](int j) {
+        for (int j = 0; j < nkv; ++j) {
           const int kv_len = min(kKTile, seq - j * kKTile);
           const uint32_t idesc_s = umma_idesc_bf16(128, (kv_len + 15) & ~15);
           mbar_wait(&k_full[ks], kph);
@@ -197,11 +196,21 @@ __global__ void __launch_bounds__(kAttnThreads, 1) pf_attention_kernel(const __g
           }
           umma_commit(&k_empty[ks]);
           if (++ks == kKS) { ks = 0; kph ^= 1; }
-        };
-        issue_qk(0);
+        }
+        umma_commit(q_empty);                                  // every QK^T of the item is issued: Q may be replaced
+      }
+    }
+  } else if (warp == 10) {
+    // ===================== PV issuer: O_t += P_t V_j (A operand = P in TMEM) =====================
+    if (lane == 0) {
+      const uint32_t idesc_o = umma_idesc_bf16(128, kHd);
+      int vs = 0;
+      uint32_t vph = 0;
+      uint32_t pfull_ph[2] = {0, 0}, ofree_ph[2] = {0, 0};
+      for (int item = blockIdx.x; item < P.n_items; item += gridDim.x) {
+        const int q0 = (item % P.n_pairs) * 2 * kQTile;
+        const int nt = (q0 + kQTile < seq) ? 2 : 1;
         for (int j = 0; j < nkv; ++j) {
-          if (j + 1 < nkv) issue_qk(j + 1);                    // overlaps the softmax of block j
-          else umma_commit(q_empty);                           // every QK^T of the item is issued: Q may be replaced
           const int nk = (min(kKTile, seq - j * kKTile) + 15) >> 4;     // 16-key MMA steps of this block
           mbar_wait(&v_full[vs], vph);
           tc_fence_after();
@@ -293,19 +302,21 @@ __global__ void __launch_bounds__(kAttnThreads, 1) pf_attention_kernel(const __g
           else if (__any_sync(0xffffffffu, m_new - m_run > kRescaleThreshold)) rescale(m_new);
           const uint64_t sc2 = pack2f(scale, scale), nm2 = pack2f(-m_run, -m_run);
           uint64_t sum_a = 0, sum_b = 0;                       // bit pattern of (+0.0f, +0.0f)
-          uint32_t pk[16];
-          softmax_chunk(s0, sc2, nm2, sum_a, sum_b, pk);
+          // all 128 probabilities first (the scores die chunk by chunk), THEN the wait for PV of block j-1 (which
+          // has had the whole softmax to complete) and the four TMEM stores back to back
+          uint32_t pk0[16], pk1[16], pk2[16], pk3[16];
+          softmax_chunk(s0, sc2, nm2, sum_a, sum_b, pk0);
+          softmax_chunk(s1, sc2, nm2, sum_a, sum_b, pk1);
+          softmax_chunk(s2, sc2, nm2, sum_a, sum_b, pk2);
+          softmax_chunk(s3, sc2, nm2, sum_a, sum_b, pk3);
           if (j > 0 && !waited) {                              // PV of block j-1 has consumed the previous P
             mbar_wait(&o_done[t], odone_ph); odone_ph ^= 1;
             tc_fence_after();
           }
-          tmem_st16(tP, pk);
-          softmax_chunk(s1, sc2, nm2, sum_a, sum_b, pk);
-          tmem_st16(tP + 16, pk);
-          softmax_chunk(s2, sc2, nm2, sum_a, sum_b, pk);
-          tmem_st16(tP + 32, pk);
-          softmax_chunk(s3, sc2, nm2, sum_a, sum_b, pk);
-          tmem_st16(tP + 48, pk);
+          tmem_st16(tP, pk0);
+          tmem_st16(tP + 16, pk1);
+          tmem_st16(tP + 32, pk2);
+          tmem_st16(tP + 48, pk3);
           float x0, x1, y0, y1;
           unpack2f(sum_a, x0, x1);
           unpack2f(sum_b, y0, y1);
@@ -423,6 +434,7 @@ extern "C" int pf_attention(const void* qk, int32_t qk_ld, const void* vt, int32
   P.scale_log2 = scale * 1.4426950408889634f;
   P.out = static_cast<__nv_bfloat16*>(out);
   P.out_ld = out_ld;
+  note_work(4.0 * B * heads * static_cast<double>(seq) * seq * kHd, "attention B%d heads%d seq%d", B, heads, seq);
   const int grid = P.n_items < sm_count[dev] ? P.n_items : sm_count[dev];
   cudaError_t le = launch_pdl(pf_attention_kernel, dim3(grid), dim3(kAttnThreads), kAttnSmem, static_cast<cudaStream_t>(stream), P);
   if (le != cudaSuccess) return set_error("pf_attention_kernel launch: %s", cudaGetErrorString(le));

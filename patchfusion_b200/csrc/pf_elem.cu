@@ -59,14 +59,20 @@ __device__ __forceinline__ void ln_row(const float* __restrict__ xr, const float
   }
 }
 
+// rows_out > 0: output row r comes from input row (r / rows_out) * rows_in + skip + r % rows_out (per-image patch
+// tokens with the cls row dropped); rows_out == 0: identity mapping.
 __global__ void layernorm_kernel(const float* __restrict__ x, int x_ld, const float* __restrict__ w,
                                  const float* __restrict__ b, float eps, int rows, int C, bf16* __restrict__ out,
-                                 int out_ld) {
+                                 int out_ld, int rows_in, int skip, int rows_out) {
   pdl_wait();
   int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
-  ln_row(x + static_cast<long long>(row) * x_ld, w, b, eps, C, out + static_cast<long long>(row) * out_ld,
-         threadIdx.x & 31);
+  long long src = row;
+  if (rows_out > 0) {
+    const int g = row / rows_out;
+    src = static_cast<long long>(g) * rows_in + skip + (row - g * rows_out);
+  }
+  ln_row(x + src * x_ld, w, b, eps, C, out + static_cast<long long>(row) * out_ld, threadIdx.x & 31);
 }
 
 // LayerNorm into the zero-padded (Hp x Wp) Swin token grid.
@@ -778,7 +784,19 @@ int pf_layernorm(const float* x, int32_t x_ld, const float* w, const float* b, f
                  void* out, int32_t out_ld, void* stream) {
   if (C % 4 || x_ld % 4 || out_ld % 4 || C > 1024) return set_error("pf_layernorm: C (<= 1024) and strides must be multiples of 4");
   cudaError_t le = launch_pdl(layernorm_kernel, dim3(nblocks(rows, 8)), dim3(256), 0, ST, x, x_ld, w, b, eps, rows, C,
-                              static_cast<bf16*>(out), out_ld);
+                              static_cast<bf16*>(out), out_ld, 0, 0, 0);
+  if (le != cudaSuccess) return set_error("layernorm_kernel launch: %s", cudaGetErrorString(le));
+  return check_launch("layernorm_kernel");
+}
+
+int pf_layernorm_grouped(const float* x, int32_t x_ld, const float* w, const float* b, float eps, int32_t groups,
+                         int32_t rows_in, int32_t skip, int32_t rows_out, int32_t C, void* out, int32_t out_ld,
+                         void* stream) {
+  if (C % 4 || x_ld % 4 || out_ld % 4 || C > 1024) return set_error("pf_layernorm_grouped: C (<= 1024) and strides must be multiples of 4");
+  if (groups < 1 || rows_out < 1 || skip < 0 || skip + rows_out > rows_in) return set_error("pf_layernorm_grouped: bad row mapping");
+  const int rows = groups * rows_out;
+  cudaError_t le = launch_pdl(layernorm_kernel, dim3(nblocks(rows, 8)), dim3(256), 0, ST, x, x_ld, w, b, eps, rows, C,
+                              static_cast<bf16*>(out), out_ld, rows_in, skip, rows_out);
   if (le != cudaSuccess) return set_error("layernorm_kernel launch: %s", cudaGetErrorString(le));
   return check_launch("layernorm_kernel");
 }

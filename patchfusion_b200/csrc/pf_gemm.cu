@@ -69,49 +69,52 @@ __device__ __forceinline__ TileCoord decode_tile(const GemmDesc& d, int t) {
 constexpr int kMaxTail = 16;   // widest fused trailing 1x1 layer
 constexpr int kTailBytes = 512 + 128 * kMaxTail * 4;   // barriers + TMEM slot + [128][kMaxTail] fp32 scratch
 
-template <bool FULL>
-__device__ __forceinline__ void epilogue_chunk(const GemmDesc& d, float (&f)[32], long long orow, int ncol, int lcol,
+// W = chunk width in accumulator columns (32, or 16 when the two warps of a quadrant split an unpaired chunk);
+// TAILN = compile-time bound on the fused trailing layer's outputs (0 = no trailing layer): keeps the executed code
+// path short - the fully unrolled 16-output variant alone is ~3k instructions and thrashed the instruction cache.
+template <bool FULL, int W, int TAILN>
+__device__ __forceinline__ void epilogue_chunk(const GemmDesc& d, float (&f)[W], long long orow, int ncol, int lcol,
                                                int nvalid, float (&y2)[kMaxTail]) {
   if (d.bias != nullptr) {
     if (FULL) {
       const float4* bp = reinterpret_cast<const float4*>(d.bias + lcol);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
+      for (int j = 0; j < W / 4; ++j) {
         float4 b = __ldg(bp + j);
         f[4 * j] += b.x; f[4 * j + 1] += b.y; f[4 * j + 2] += b.z; f[4 * j + 3] += b.w;
       }
     } else {
 #pragma unroll
-      for (int j = 0; j < 32; ++j) if (j < nvalid) f[j] += __ldg(d.bias + lcol + j);
+      for (int j = 0; j < W; ++j) if (j < nvalid) f[j] += __ldg(d.bias + lcol + j);
     }
   }
   if (d.act == PF_ACT_RELU) {
 #pragma unroll
-    for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.0f);
+    for (int j = 0; j < W; ++j) f[j] = fmaxf(f[j], 0.0f);
   } else if (d.act == PF_ACT_GELU) {
 #pragma unroll
-    for (int j = 0; j < 32; ++j) if (FULL || j < nvalid) f[j] = gelu_erf(f[j]);
+    for (int j = 0; j < W; ++j) if (FULL || j < nvalid) f[j] = gelu_erf(f[j]);
   } else if (d.act == PF_ACT_SOFTPLUS) {
 #pragma unroll
-    for (int j = 0; j < 32; ++j) if (FULL || j < nvalid) f[j] = softplus(f[j]);
+    for (int j = 0; j < W; ++j) if (FULL || j < nvalid) f[j] = softplus(f[j]);
   }
   // fused trailing 1x1 layer: y[i] += sum_j W2[i][lcol + j] * f[j]  (row-local: the thread owns the whole row)
-  if (d.w2 != nullptr) {
+  if (TAILN > 0) {
 #pragma unroll
-    for (int i = 0; i < kMaxTail; ++i) {
+    for (int i = 0; i < TAILN; ++i) {
       if (i < d.n2) {
         const float* wp = d.w2 + static_cast<long long>(i) * d.n_logical + lcol;
         float a = 0.f;
         if (FULL) {
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
+          for (int j = 0; j < W / 4; ++j) {
             float4 w4 = __ldg(reinterpret_cast<const float4*>(wp) + j);
             a = fmaf(w4.x, f[4 * j], a); a = fmaf(w4.y, f[4 * j + 1], a);
             a = fmaf(w4.z, f[4 * j + 2], a); a = fmaf(w4.w, f[4 * j + 3], a);
           }
         } else {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) if (j < nvalid) a = fmaf(__ldg(wp + j), f[j], a);
+          for (int j = 0; j < W; ++j) if (j < nvalid) a = fmaf(__ldg(wp + j), f[j], a);
         }
         y2[i] += a;
       }
@@ -125,7 +128,7 @@ __device__ __forceinline__ void epilogue_chunk(const GemmDesc& d, float (&f)[32]
     const __nv_bfloat16* rp = rbase + orow * d.res_ld + lcol;
     if (FULL) {
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
+      for (int j = 0; j < W / 8; ++j) {
         uint4 u = __ldg(reinterpret_cast<const uint4*>(rp) + j);
         const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
 #pragma unroll
@@ -136,7 +139,7 @@ __device__ __forceinline__ void epilogue_chunk(const GemmDesc& d, float (&f)[32]
       }
     } else {
 #pragma unroll
-      for (int j = 0; j < 32; ++j) if (j < nvalid) f[j] += __bfloat162float(rp[j]);
+      for (int j = 0; j < W; ++j) if (j < nvalid) f[j] += __bfloat162float(rp[j]);
     }
   }
   const int oc = lcol + d.out_col0;      // physical output column
@@ -146,14 +149,14 @@ __device__ __forceinline__ void epilogue_chunk(const GemmDesc& d, float (&f)[32]
     const int b = m / d.vt_seq, tok = m - b * d.vt_seq;
     __nv_bfloat16* vp = d.vt + (static_cast<long long>(b) * d.vt_dim + (ncol - d.vt_col0)) * d.vt_seq_pad + tok;
 #pragma unroll
-    for (int j = 0; j < 32; ++j)
+    for (int j = 0; j < W; ++j)
       if (FULL || j < nvalid) vp[static_cast<long long>(j) * d.vt_seq_pad] = __float2bfloat16(f[j]);
   } else if (d.gamma != nullptr) {
     // x <- x + gamma * (acc + bias): fp32 residual stream updated in place
     float* xp = reinterpret_cast<float*>(d.out) + orow * d.out_ld + oc;
     if (FULL) {
 #pragma unroll
-      for (int j = 0; j < 32; j += 4) {
+      for (int j = 0; j < W; j += 4) {
         float4 xv = *reinterpret_cast<float4*>(xp + j);
         float4 g = __ldg(reinterpret_cast<const float4*>(d.gamma + lcol + j));
         xv.x += g.x * f[j]; xv.y += g.y * f[j + 1]; xv.z += g.z * f[j + 2]; xv.w += g.w * f[j + 3];
@@ -161,43 +164,75 @@ __device__ __forceinline__ void epilogue_chunk(const GemmDesc& d, float (&f)[32]
       }
     } else {
 #pragma unroll
-      for (int j = 0; j < 32; ++j) if (j < nvalid) xp[j] += __ldg(d.gamma + lcol + j) * f[j];
+      for (int j = 0; j < W; ++j) if (j < nvalid) xp[j] += __ldg(d.gamma + lcol + j) * f[j];
     }
   } else if (d.out_f32) {
     float* op = reinterpret_cast<float*>(d.out) + orow * d.out_ld + oc;
     if (FULL) {
 #pragma unroll
-      for (int j = 0; j < 32; j += 4)
+      for (int j = 0; j < W; j += 4)
         *reinterpret_cast<float4*>(op + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
     } else {
 #pragma unroll
-      for (int j = 0; j < 32; ++j) if (j < nvalid) op[j] = f[j];
+      for (int j = 0; j < W; ++j) if (j < nvalid) op[j] = f[j];
     }
   } else {
     __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(d.out) + orow * d.out_ld + oc;
     if (FULL) {
 #pragma unroll
-      for (int j = 0; j < 32; j += 8)
+      for (int j = 0; j < W; j += 8)
         *reinterpret_cast<uint4*>(op + j) = make_uint4(pack_bf16(f[j], f[j + 1]), pack_bf16(f[j + 2], f[j + 3]),
                                                         pack_bf16(f[j + 4], f[j + 5]), pack_bf16(f[j + 6], f[j + 7]));
     } else {
 #pragma unroll
-      for (int j = 0; j < 32; ++j) if (j < nvalid) op[j] = __float2bfloat16(f[j]);
+      for (int j = 0; j < W; ++j) if (j < nvalid) op[j] = __float2bfloat16(f[j]);
     }
     if (d.out2 != nullptr) {
       __nv_bfloat16* o2 = d.out2 + orow * d.out2_ld + lcol;
       if (FULL) {
 #pragma unroll
-        for (int j = 0; j < 32; j += 8)
+        for (int j = 0; j < W; j += 8)
           *reinterpret_cast<uint4*>(o2 + j) =
               make_uint4(pack_bf16(fmaxf(f[j], 0.f), fmaxf(f[j + 1], 0.f)), pack_bf16(fmaxf(f[j + 2], 0.f), fmaxf(f[j + 3], 0.f)),
                          pack_bf16(fmaxf(f[j + 4], 0.f), fmaxf(f[j + 5], 0.f)), pack_bf16(fmaxf(f[j + 6], 0.f), fmaxf(f[j + 7], 0.f)));
       } else {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) if (j < nvalid) o2[j] = __float2bfloat16(fmaxf(f[j], 0.0f));
+        for (int j = 0; j < W; ++j) if (j < nvalid) o2[j] = __float2bfloat16(fmaxf(f[j], 0.0f));
       }
     }
   }
+}
+
+// one W-column chunk starting at accumulator column cb of this thread's row
+template <int W, int TAILN>
+__device__ __forceinline__ void epilogue_cols(const GemmDesc& d, uint32_t taddr, int cb, const TileCoord& c, int ocol0,
+                                              long long orow, bool row_ok, float (&y2)[kMaxTail]) {
+  uint32_t v[W];
+  if (W == 32) tmem_ld32(taddr + cb, reinterpret_cast<uint32_t (&)[32]>(v));
+  else tmem_ld16(taddr + cb, reinterpret_cast<uint32_t (&)[16]>(v));
+  tmem_ld_wait();
+  if (!row_ok) return;
+  const int ncol = c.n0 + cb;            // global N index of v[0] (selects the V^T path)
+  const int lcol = ocol0 + cb;           // logical output channel of v[0] (bias / gamma / residual index)
+  const int nvalid = min(W, d.n_logical - lcol);   // columns of this chunk that exist
+  if (nvalid <= 0) return;
+  float f[W];
+#pragma unroll
+  for (int j = 0; j < W; ++j) f[j] = __uint_as_float(v[j]);
+  if (nvalid == W) epilogue_chunk<true, W, TAILN>(d, f, orow, ncol, lcol, W, y2);
+  else epilogue_chunk<false, W, TAILN>(d, f, orow, ncol, lcol, nvalid, y2);
+}
+
+// All column chunks of one accumulator row pair of warps: the two warps of a TMEM lane quadrant take alternate
+// 32-column chunks; an unpaired last chunk (block_n = 32, 96, 160, 224) is split 16 / 16 so both warps carry the
+// same load (the activation + fused-tail work of the clb / N = 32 layers is epilogue-bound).
+template <int TAILN>
+__device__ __forceinline__ void epilogue_row(const GemmDesc& d, uint32_t taddr, int half, const TileCoord& c, int ocol0,
+                                             long long orow, bool row_ok, float (&y2)[kMaxTail]) {
+  const int nchunks = d.block_n >> 5;
+  const int paired = nchunks & ~1;
+  for (int ch = half; ch < paired; ch += 2) epilogue_cols<32, TAILN>(d, taddr, ch * 32, c, ocol0, orow, row_ok, y2);
+  if (nchunks & 1) epilogue_cols<16, TAILN>(d, taddr, paired * 32 + half * 16, c, ocol0, orow, row_ok, y2);
 }
 
 // Epilogue warps (4 warps, TMEM lane quadrant = warp & 3): drain accumulator stage `acc` of each tile this CTA owns.
@@ -241,24 +276,10 @@ __device__ __forceinline__ void epilogue_loop(const GemmDesc& d, int total_tiles
     float y2[kMaxTail];
 #pragma unroll
     for (int i = 0; i < kMaxTail; ++i) y2[i] = 0.f;
-    for (int cb = half * 32; cb < d.block_n; cb += 64) {
-      uint32_t v[32];
-      tmem_ld32(taddr + cb, v);
-      tmem_ld_wait();
-      if (!row_ok) continue;
-      const int ncol = c.n0 + cb;            // global N index of v[0] (selects the V^T path)
-      const int lcol = ocol0 + cb;           // logical output channel of v[0] (bias / gamma / residual index)
-      const int nvalid = min(32, d.n_logical - lcol);   // columns of this chunk that exist
-      if (nvalid <= 0) continue;
-      float f[32];
-#pragma unroll
-      for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-      if (nvalid == 32) {
-        epilogue_chunk<true>(d, f, orow, ncol, lcol, 32, y2);
-      } else {
-        epilogue_chunk<false>(d, f, orow, ncol, lcol, nvalid, y2);
-      }
-    }
+    if (d.w2 == nullptr) epilogue_row<0>(d, taddr, half, c, ocol0, orow, row_ok, y2);
+    else if (d.n2 <= 1) epilogue_row<1>(d, taddr, half, c, ocol0, orow, row_ok, y2);
+    else if (d.n2 <= 4) epilogue_row<4>(d, taddr, half, c, ocol0, orow, row_ok, y2);
+    else epilogue_row<kMaxTail>(d, taddr, half, c, ocol0, orow, row_ok, y2);
     if (d.w2 != nullptr) {
       // combine the two half-row partial sums of the fused trailing layer through shared memory
       float* ts = tail_smem + r * kMaxTail;
@@ -583,6 +604,15 @@ int gemm_launch(const GemmDesc& d, const CUtensorMap* tmA, const CUtensorMap& tm
   }
   const int g_sm_count = g_sm_counts[dev];
   if (d.block_n % 32 != 0 || d.block_n < 32 || d.block_n > 256) return set_error("gemm: bad block_n %d", d.block_n);
+  {
+    const long long rows = d.a_mode == 1 ? static_cast<long long>(d.NB) * d.H * d.W : d.M;
+    int ktrue = 0;
+    for (int s = 0; s < d.num_src; ++s) ktrue += d.k_true[s];
+    const int n_true = d.ps > 1 ? d.n_logical * d.ps * d.ps : d.N;
+    note_work(2.0 * rows * ktrue * d.taps * n_true, "%s rows%lld K%dx%d N%d%s%s%s", d.taps == 9 ? "conv3x3" : (d.a_mode == 1 ? "conv1x1" : (d.ps > 1 ? "convT" : "linear")),
+              rows, d.taps, ktrue, n_true, d.act ? (d.act == PF_ACT_GELU ? " gelu" : (d.act == PF_ACT_RELU ? " relu" : " softplus")) : "",
+              d.gamma ? " gamma" : (d.vt ? " vt" : ""), d.w2 ? " tail" : "");
+  }
   GemmKernelParams P;
   for (int s = 0; s < d.num_src; ++s) P.tmA[s] = tmA[s];
   for (int s = d.num_src; s < 3; ++s) P.tmA[s] = tmA[0];
@@ -624,7 +654,7 @@ int gemm_launch(const GemmDesc& d, const CUtensorMap* tmA, const CUtensorMap& tm
   }
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_error("pf_gemm_kernel launch: %s", cudaGetErrorString(e));
-  count_launch();
+  count_launch(d.halo ? "pf_conv3_halo_kernel" : "pf_gemm_kernel");
   return 0;
 }
 

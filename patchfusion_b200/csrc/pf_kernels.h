@@ -12,6 +12,7 @@ struct GemmDesc {
   int num_src, a_mode, taps;
   int halo;              // 3x3 conv through the halo-tile kernel (bh=16, bw=8)
   int chunks[3];
+  int k_true[3];         // logical channels of each source (profiler flop count)
   int M, NB, H, W, bh, bw, tiles_y, tiles_x, m_tiles;
   int N, block_n, n_tiles;
   const float* bias;
@@ -61,7 +62,9 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
   cfg.numAttrs = pdl_enabled() ? 1 : 0;
   return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
-void count_launch();
+void count_launch(const char* name);
+// profiler hint for the NEXT launch: algorithmic flops + a printf-style shape label (no-op unless profiling)
+void note_work(double flops, const char* fmt, ...);
 int check_launch(const char* what);
 
 int gemm_launch(const GemmDesc& d, const CUtensorMap* tmA, const CUtensorMap& tmB, cudaStream_t stream);

@@ -1,7 +1,8 @@
-"""Device-side execution of the PatchFusion hot path on the libpf_b200 kernels.
+"""Device-side execution of the PatchFusion hot path on libpf_b200.
 
-`Engine` owns the packed weights and a pool of persistent device buffers (static addresses: TMA tensor maps are
-cached per buffer and the whole per-micro-batch sequence is CUDA-graph capturable).  It sequences the kernels for
+`Engine` packs the weights once (pf_pack_weight), describes them to the library as C structs (patchfusion_b200/stage.py
+<-> include/pf_b200.h) and owns the workspaces; the kernel SEQUENCES live inside the library
+(csrc/pf_stage.cu: pf_branch_forward / pf_g2l_forward / pf_fusion_forward), one call per stage:
 
     coarse/fine branch   reference `estimator/models/patchfusion.py:189-225` -> zoedepth_v1.py:125-233 ->
                          depth_anything.py:262-278 -> dpt.py:97-157 -> dinov2 vision_transformer.py:297-321
@@ -11,7 +12,8 @@ cached per buffer and the whole per-micro-batch sequence is CUDA-graph capturabl
     tiling / stitch      `estimator/models/baseline_pretrain.py:143-331`, estimator/models/utils.py:21-47
 
 Nothing here touches torch for arithmetic on the path: torch allocates memory, owns the stream, and runs the
-one-off load-time transforms (pos-embed bicubic resample, BatchNorm folding constants).
+one-off load-time transforms (pos-embed bicubic resample, BatchNorm folding constants).  Workspace addresses are a
+function of (weights, batch) only, so TMA tensor maps are cached and every stage call is CUDA-graph capturable.
 """
 import ctypes as ct
 import math
@@ -55,6 +57,9 @@ class Engine:
         self.bcfg = {'coarse': _get(config, 'coarse_branch'), 'fine': _get(config, 'fine_branch')}
         self.gf = guided_fusion_hparams(_get(config, 'guided_fusion'), self.P)
         self.bufs = {}
+        self.arenas = {}
+        self.generation = 0
+        self._keep = []
         self.sd = {k: v.to(self.dev) for k, v in state_dict.items()}
         H, W = self.P
         assert H % 14 == 0 and W % 14 == 0
@@ -62,6 +67,8 @@ class Engine:
         self.W = {}
         self._pack_all()
         self.sd = None   # fp32 originals are no longer needed on the device
+        self.c_branch = {'coarse': self._c_branch('coarse'), 'fine': self._c_branch('fine')}
+        self.c_fusion = self._c_fusion()
 
     # ------------------------------------------------------------------ buffers
     def buf(self, key, shape, dtype=BF16):
@@ -219,283 +226,193 @@ class Engine:
         self.W['fusion'] = self._pack_fusion()
         torch.cuda.synchronize(self.dev)
 
-    # ------------------------------------------------------------------ small helpers
-    def conv(self, key, pw, srcs, N=None, act=ACT_NONE, res1=None, res2=None, relu_copy=False, out=None,
-             out_dtype=BF16, tail=None, tail_out=None, skip_main=False):
-        """3x3 / 1x1 conv over NHWC maps `srcs` (list of Map) -> Map (and optionally its ReLU copy)."""
-        B, (h, w) = srcs[0].B, srcs[0].hw
-        N = pw.N if N is None else N
-        if out is None:
-            out = Map(self.buf(key, (B, h, w, pad_to(N, 8)), out_dtype), N)
-        o2 = Map(self.buf(key + '.relu', (B, h, w, pad_to(N, 8))), N) if relu_copy else None
-        ops.gemm(pw, [s.t for s in srcs], out.t, image=(B, h, w), act=act,
-                 res1=res1.t if res1 is not None else None, res2=res2.t if res2 is not None else None,
-                 out2=o2.t if o2 is not None else None, src_c=[s.C for s in srcs], tail=tail, tail_out=tail_out,
-                 skip_main=skip_main)
-        return (out, o2) if relu_copy else out
+    # ------------------------------------------------------------------ C structs for the stage-level ABI
+    def _c_head(self, Wh, hp, bcfg, has_rel):
+        from . import stage
+        H = stage.PfHead()
 
-    def resize(self, key, x, size, out=None, out_col0=0):
-        if out is None and x.hw == tuple(size):
-            return x
-        if out is None:
-            out = self.map(key, x.B, size[0], size[1], x.C)
-        ops.resize_bilinear(x.t, x.C, size[0], size[1], out.t, out_col0=out_col0)
-        return out
+        def L(name):
+            return stage.layer(Wh[name], Wh.get(name[:-2] + '.tail') if name.endswith('.0') else None)
 
-    # ------------------------------------------------------------------ one branch
-    def branch(self, which, images, taps=None, slot=''):
-        """images: planar fp32 [B,3,H,W] in [0,1] (un-normalised).  Returns (depth fp32 [B,H,W], feats[6] Maps
-        low->high: x_d0, r4, r3, r2, r1, out_conv).  `slot` selects an independent buffer set (double buffering of
-        the fine branch against the fusion stage of the previous micro-batch)."""
+        H.seed0, H.seed2 = L('seed_bin_regressor.0'), L('seed_bin_regressor.2')
+        H.seedproj0, H.seedproj2 = L('seed_projector.0'), L('seed_projector.2')
+        for i in range(4):
+            H.proj0[i], H.proj2[i] = L('projectors.%d.0' % i), L('projectors.%d.2' % i)
+            H.att0[i], H.att2[i] = L('attractors.%d.0' % i), L('attractors.%d.2' % i)
+            H.n_attractors[i] = hp['n_attractors'][i]
+        H.clb0 = stage.layer(Wh['clb.0'], Wh['clb.tail'])
+        H.n_bins, H.bin_embedding_dim = hp['n_bins'], hp['bin_embedding_dim']
+        H.attractor_flags = (1 if hp['attractor_kind'] == 'mean' else 0) | (2 if hp['attractor_type'] == 'exp' else 0)
+        H.has_rel = 1 if has_rel else 0
+        H.min_temp, H.max_temp = float(_get(bcfg, 'min_temp')), float(_get(bcfg, 'max_temp'))
+        return H
+
+    def _c_branch(self, which):
+        from . import stage
         Wd, hp = self.W[which], self.hp[which]
-        B = images.shape[0]
-        H, Wd_ = self.P
-        gh, gw, D, C, oc = self.gh, self.gw, hp['dim'], hp['features'], hp['out_channels']
-        npatch, seq = gh * gw, gh * gw + 1
-        seq_pad = pad_to(seq, 8)
-        k = which + slot + '.'
-        st = stream_ptr()
-        # ---- tokens
-        a0 = self.buf(k + 'im2col', (B * npatch, 592))
-        call('pf_patch_im2col', images, B, H, Wd_, a0, 592, st)
-        patch = self.buf(k + 'patch', (B * npatch, D), F32)
-        ops.gemm(Wd['patch'], [a0], patch, src_c=[592])
-        x = self.buf(k + 'x', (B * seq, D), F32)
-        call('pf_assemble_tokens', patch, Wd['cls'], Wd['pos'], B, npatch, D, x, st)
-        if taps is not None:
-            taps['tokens'] = x.clone()
-        hbuf = self.buf(k + 'h', (B * seq, D))
-        qk = self.buf(k + 'qk', (B * seq, 2 * D))
-        vt = self.buf(k + 'vt', (B * D, seq_pad))
-        att = self.buf(k + 'att', (B * seq, D))
-        hid = self.buf(k + 'hid', (B * seq, 4 * D))
-        feats = []
+        B = stage.PfBranch()
+        B.H, B.W = self.P
+        B.dim, B.depth, B.heads, B.features = hp['dim'], hp['depth'], hp['heads'], hp['features']
+        for i in range(4):
+            B.out_channels[i] = hp['out_channels'][i]
+        B.patch = stage.layer(Wd['patch'])
+        B.pos, B.cls = Wd['pos'].data_ptr(), Wd['cls'].data_ptr()
+        blocks = (stage.PfVitBlock * hp['depth'])()
         for i in range(hp['depth']):
-            bw = Wd['b%d' % i]
-            ops.layernorm(x, bw['n1w'], bw['n1b'], 1e-6, hbuf)
-            ops.gemm(bw['qkv'], [hbuf], qk, vt=vt, vt_col0=2 * D, vt_seq=seq, vt_seq_pad=seq_pad)
-            ops.attention(qk, vt, B, seq, seq_pad, hp['heads'], 64 ** -0.5, att)
-            ops.gemm(bw['proj'], [att], x, gamma=bw['ls1'])
-            ops.layernorm(x, bw['n2w'], bw['n2b'], 1e-6, hbuf)
-            ops.gemm(bw['fc1'], [hbuf], hid, act=ACT_GELU)
-            ops.gemm(bw['fc2'], [hid], x, gamma=bw['ls2'])
-            if taps is not None:
-                taps['block%d' % i] = x.clone()
-            if i >= hp['depth'] - 4:
-                f = self.buf(k + 'vitout%d' % len(feats), (B, gh, gw, D))
-                for b in range(B):      # final LayerNorm of the patch tokens only (cls row skipped)
-                    call('pf_layernorm', x[b * seq + 1:], D, Wd['nw'], Wd['nb'], ct.c_float(1e-6), npatch, D,
-                         f[b], D, st)
-                feats.append(Map(f, D))
-        return self.dpt_and_head(which, feats, taps, slot)
-
-    def dpt_and_head(self, which, feats, taps=None, slot=''):
-        Wd, hp = self.W[which], self.hp[which]
-        B = feats[0].B
-        gh, gw, C, oc = self.gh, self.gw, hp['features'], hp['out_channels']
-        H, Wimg = self.P
-        k = which + slot + '.dpt.'
-        st = stream_ptr()
-        lay = []
+            bw, cb = Wd['b%d' % i], blocks[i]
+            for k in ('n1w', 'n1b', 'n2w', 'n2b', 'ls1', 'ls2'):
+                setattr(cb, k, bw[k].data_ptr())
+            for k in ('qkv', 'proj', 'fc1', 'fc2'):
+                setattr(cb, k, stage.layer(bw[k]))
+        self._keep.append(blocks)
+        B.blocks = blocks
+        B.nw, B.nb = Wd['nw'].data_ptr(), Wd['nb'].data_ptr()
         for i in range(4):
-            p = self.map(k + 'proj%d' % i, B, gh, gw, oc[i])
-            ops.gemm(Wd['proj%d' % i], [feats[i].rows()], p.rows())
-            if i == 0:
-                o = self.map(k + 'rs0', B, gh * 4, gw * 4, oc[0])
-                ops.gemm_convT(Wd['rs0'], p.rows(), (B, gh, gw), o.t)
-            elif i == 1:
-                o = self.map(k + 'rs1', B, gh * 2, gw * 2, oc[1])
-                ops.gemm_convT(Wd['rs1'], p.rows(), (B, gh, gw), o.t)
-            elif i == 2:
-                o = p
-            else:
-                oh, ow = (gh - 1) // 2 + 1, (gw - 1) // 2 + 1
-                col = self.buf(k + 'rs3col', (B * oh * ow, 9 * oc[3]))
-                call('pf_im2col_3x3_s2', p.t, B, gh, gw, oc[3], p.t.shape[-1], col, st)
-                o = self.map(k + 'rs3', B, oh, ow, oc[3])
-                ops.gemm(Wd['rs3'], [col], o.rows())
-            lay.append(o)
-        rn, rn_relu = [], []
-        for i in range(4):
-            a, b = self.conv(k + 'rn%d' % i, Wd['rn%d' % i], [lay[i]], relu_copy=True)
-            rn.append(a)
-            rn_relu.append(b)
+            B.proj[i] = stage.layer(Wd['proj%d' % i])
+            B.rn[i] = stage.layer(Wd['rn%d' % i])
+            B.ff_out[i] = stage.layer(Wd['ff%d.out' % (i + 1)])
+            for u in (1, 2):
+                B.ff_c1[i][u - 1] = stage.layer(Wd['ff%d.u%d.c1' % (i + 1, u)])
+                B.ff_c2[i][u - 1] = stage.layer(Wd['ff%d.u%d.c2' % (i + 1, u)])
+        B.rs0, B.rs1, B.rs3 = stage.layer(Wd['rs0']), stage.layer(Wd['rs1']), stage.layer(Wd['rs3'])
+        B.oc1 = stage.layer(Wd['oc1'])
+        B.oc2 = stage.layer(Wd['oc2.0'], Wd['oc2.tail'])
+        B.conv2 = stage.layer(Wd['conv2'])
+        B.head = self._c_head(Wd['head'], hp, self.bcfg[which], True)
+        return B
 
-        def rcu(tag, wi, u, x, x_relu, extra=None, relu_copy=False):
-            t = self.conv(k + tag + '.t', Wd['ff%d.u%d.c1' % (wi, u)], [x_relu], act=ACT_RELU)
-            return self.conv(k + tag + '.y', Wd['ff%d.u%d.c2' % (wi, u)], [t], res1=x, res2=extra, relu_copy=relu_copy)
-
-        def ffb(wi, path, skip, skip_relu, size):
-            if path is None:
-                s, s_relu = skip, skip_relu
-            else:
-                s, s_relu = rcu('ff%d.u1' % wi, wi, 1, skip, skip_relu, extra=path, relu_copy=True)
-            y = rcu('ff%d.u2' % wi, wi, 2, s, s_relu)
-            # out_conv (1x1) commutes with the bilinear upsample: run it at the low resolution
-            y = self.conv(k + 'ff%d.out' % wi, Wd['ff%d.out' % wi], [y])
-            return self.resize(k + 'ff%d.up' % wi, y, size)
-
-        p4 = ffb(4, None, rn[3], rn_relu[3], rn[2].hw)
-        p3 = ffb(3, p4, rn[2], rn_relu[2], rn[1].hw)
-        p2 = ffb(2, p3, rn[1], rn_relu[1], rn[0].hw)
-        p1 = ffb(1, p2, rn[0], rn_relu[0], (rn[0].hw[0] * 2, rn[0].hw[1] * 2))
-        o = self.conv(k + 'oc1', Wd['oc1'], [p1])
-        o = self.resize(k + 'oc1up', o, (H, Wimg))
-        rel = Map(self.buf(k + 'rel', (B, H, Wimg, 8), F32), 1)
-        # output_conv2: 3x3 C/2->32 + ReLU (the hooked `out_conv` tap) with the 1x1 32->1 + ReLU fused in its epilogue
-        out_conv = self.conv(k + 'oc2', Wd['oc2.0'], [o], act=ACT_RELU,
-                             tail=Wd['oc2.tail'] + (ACT_RELU,), tail_out=rel.t)
-        x_d0 = self.conv(k + 'xd0', Wd['conv2'], [rn[3]])
-        blocks = [p4, p3, p2, p1]
-        if taps is not None:
-            taps['rel'] = rel.t[..., 0].clone()
-        depth = self.metric_head(which + slot + '.head.', Wd['head'], hp, self.bcfg[which], x_d0, blocks, out_conv, rel, taps)
-        return depth, [x_d0] + blocks + [out_conv]
-
-    def metric_head(self, k, Wh, hp, bcfg, x, x_blocks, last, rel, taps=None, depth_out=None):
-        """zoedepth_v1.py:173-219 / patchfusion.py:297-339.  rel: Map fp32 [B,H,W,8] (col 0) or None."""
-        st = stream_ptr()
-        B = x.B
-        nb, E = hp['n_bins'], hp['bin_embedding_dim']
-
-        def mlp(tag, name, src, act2=ACT_NONE, f32_out=False, n_out=None):
-            pw = Wh[name + '.2']
-            if f32_out and (name + '.tail') in Wh:
-                h, w = src.hw
-                o = Map(self.buf(k + tag + '.o', (B, h, w, pad_to(pad_to(pw.N, 8), 32)), F32), pw.N)
-                self.conv(k + tag + '.t', Wh[name + '.0'], [src], act=ACT_RELU, tail=Wh[name + '.tail'] + (act2,),
-                          tail_out=o.t, skip_main=True)
-                return o
-            t = self.conv(k + tag + '.t', Wh[name + '.0'], [src], act=ACT_RELU)
-            if f32_out:
-                h, w = src.hw
-                o = Map(self.buf(k + tag + '.o', (B, h, w, pad_to(pad_to(pw.N, 8), 32)), F32), pw.N)
-                ops.gemm(pw, [t.t], o.t, image=(B, h, w), act=act2, src_c=[t.C])
-                return o
-            return self.conv(k + tag + '.o', pw, [t], act=act2)
-
-        b_prev = mlp('seed', 'seed_bin_regressor', x, ACT_SOFTPLUS, f32_out=True)      # fp32 [B,h,w,64]
-        prev_emb = mlp('seedproj', 'seed_projector', x)
-        ph, pw_ = x.hw
-        b_t = b_prev.t
-        for i, xb in enumerate(x_blocks):
-            h, w = xb.hw
-            emb = mlp('proj%d' % i, 'projectors.%d' % i, xb)
-            s = self.map(k + 'sum%d' % i, B, h, w, E)
-            call('pf_add_upsampled', emb.t, B, h, w, E, prev_emb.t, prev_emb.hw[0], prev_emb.hw[1], s.t, st)
-            A = mlp('att%d' % i, 'attractors.%d' % i, s, ACT_SOFTPLUS, f32_out=True)
-            b_new = self.buf(k + 'b%d' % i, (B, h, w, nb), F32)
-            call('pf_attractor', A.t, A.t.shape[-1], hp['n_attractors'][i], b_t, ph, pw_, B, h, w, nb,
-                 (1 if hp['attractor_kind'] == 'mean' else 0) | (2 if hp['attractor_type'] == 'exp' else 0), b_new, st)
-            b_t, ph, pw_, prev_emb = b_new, h, w, emb
-            if taps is not None:
-                taps['b%d' % i] = b_new.clone()
-        H, Wimg = last.hw
-        emb_up = self.resize(k + 'embup', prev_emb, (H, Wimg))
-        if rel is not None:
-            relb = self.map(k + 'relb', B, H, Wimg, 1)
-            call('pf_f32_to_bf16', rel.t, ct.c_int64(rel.t.numel()), relb.t, st)
-            srcs = [last, relb, emb_up]
-        else:
-            srcs = [last, emb_up]
-        pt = self.buf(k + 'pt', (B, H, Wimg, 8), F32)
-        # CLB MLP: 1x1 (161->80) + GELU with the 80->4 + Softplus layer fused in its epilogue (dist_layers.py:91-98)
-        self.conv(k + 'clb0', Wh['clb.0'], srcs, act=ACT_GELU, tail=Wh['clb.tail'] + (ACT_SOFTPLUS,), tail_out=pt,
-                  skip_main=True)
-        depth = self.buf(k + 'depth', (B, H, Wimg), F32) if depth_out is None else depth_out
-        assert depth.dtype == F32 and depth.is_contiguous() and tuple(depth.shape) == (B, H, Wimg)
-        call('pf_logbinom_depth', pt, 8, b_t, ph, pw_, B, H, Wimg, nb, ct.c_float(_get(bcfg, 'min_temp')),
-             ct.c_float(_get(bcfg, 'max_temp')), depth, st)
-        return depth
-
-    # ------------------------------------------------------------------ G2L (once per image)
-    def g2l(self, coarse_feats):
+    def _c_fusion(self):
+        from . import stage
         Wf = self.W['fusion']
-        st = stream_ptr()
-        outs = []
-        for i, f in enumerate(coarse_feats):
-            L = Wf['g2l%d' % i]
-            c, heads = L['C'], L['heads']
-            h, w = f.hw
-            n = h * w
-            Hp, Wp = math.ceil(h / WINDOW) * WINDOW, math.ceil(w / WINDOW) * WINDOW
-            k = 'g2l%d.' % i
-            x = self.buf(k + 'x', (n, c), F32)
-            # the reference adds absolute_pos_embed (1, num_patches, C) to the (1, h*w, C) tokens (swin_layers.py:421-422)
-            # and would fail on the broadcast if they differ
-            assert L['ape'].shape[0] == n, 'guided_fusion.num_patches[%d] = %d does not match the %dx%d coarse map' % (
-                i, L['ape'].shape[0], h, w)
-            call('pf_g2l_embed', f.t, f.t.shape[-1], L['ape'], n, c, x, st)
-            npad = self.buf(k + 'npad', (Hp * Wp, c))
-            qkv = self.buf(k + 'qkv', (Hp * Wp, 3 * c))
-            att = self.buf(k + 'att', (Hp * Wp, c))
-            prj = self.buf(k + 'prj', (Hp * Wp, c), F32)
-            hb = self.buf(k + 'h', (n, c))
-            hid = self.buf(k + 'hid', (n, 4 * c))
-            for bi, bw in enumerate(L['blocks']):
-                shift = 0 if bi % 2 == 0 else WINDOW // 2
-                call('pf_swin_norm_pad', x, bw['n1w'], bw['n1b'], ct.c_float(1e-5), h, w, Hp, Wp, c, npad, st)
-                ops.gemm(bw['qkv'], [npad], qkv)
-                call('pf_window_attention', qkv, bw['table'], Hp, Wp, c, heads, shift, att, st)
-                ops.gemm(bw['proj'], [att], prj)
-                call('pf_swin_residual_crop', x, prj, h, w, Wp, c, st)
-                ops.layernorm(x, bw['n2w'], bw['n2b'], 1e-5, hb)
-                ops.gemm(bw['fc1'], [hb], hid, act=ACT_GELU)
-                ops.gemm(bw['fc2'], [hid], x, gamma=L['ones'])
-            o = self.map(k + 'out', 1, h, w, c)
-            ops.layernorm(x, L['nw'], L['nb'], 1e-5, o.rows())
-            outs.append(o)
-        return outs
-
-    # ------------------------------------------------------------------ fusion of T tiles
-    def fusion(self, crops, boxes, fine_depth, fine_feats, coarse_depth, coarse_feats, g2l_maps, taps=None,
-               depth_out=None):
-        """crops planar fp32 [T,3,H,W]; boxes fp32 [T,4] (device, patch_process units); returns fp32 [T,H,W]."""
-        Wf = self.W['fusion']
-        st = stream_ptr()
-        T = crops.shape[0]
-        H, Wimg = self.P
-        k = 'fus.'
-        # ROI crop-zoom of the whole-image coarse maps, fused 3x3 convs with the fine maps (patchfusion.py:263-267)
-        guide = []
+        F_ = stage.PfFusion()
+        F_.H, F_.W = self.P
         for i in range(5):
-            cf = coarse_feats[i]
-            h, w = cf.hw
-            roi = self.map(k + 'croi%d' % i, T, h, w, cf.C)
-            ops.roi_crop_zoom(cf.t, cf.C, boxes, h / self.P[0], roi.t)
-            guide.append(self.conv(k + 'guide%d' % i, Wf['fc%d' % i], [roi, fine_feats[i]]))
-        droi = self.buf(k + 'droi', (T, H, Wimg), F32)
-        ops.roi_crop_zoom(coarse_depth, 1, boxes, 1.0, droi)
-        u = self.map(k + 'unet_in', T, H, Wimg, 5)
-        call('pf_pack_unet_input', droi, fine_depth, crops, T, H, Wimg, u.t, 8, st)
-        # encoder
-        x = self.conv(k + 'inc0', Wf['inc.0'], [u], act=ACT_RELU)
-        x = self.conv(k + 'inc1', Wf['inc.1'], [x], act=ACT_RELU)
-        enc = [x]
-        for i in range(5):
-            h, w = x.hw
-            p = self.map(k + 'pool%d' % i, T, h // 2, w // 2, x.C)
-            ops.maxpool2(x.t, x.C, p.t)
-            x = self.conv(k + 'down%d.0' % i, Wf['down%d.0' % i], [p], act=ACT_RELU)
-            x = self.conv(k + 'down%d.1' % i, Wf['down%d.1' % i], [x], act=ACT_RELU)
-            enc.append(x)
-        enc = enc[::-1]
-        outs, prev = [], None
+            F_.fc[i] = stage.layer(Wf['fc%d' % i])
+            F_.down[i][0], F_.down[i][1] = stage.layer(Wf['down%d.0' % i]), stage.layer(Wf['down%d.1' % i])
+            F_.up[i][0], F_.up[i][1] = stage.layer(Wf['up%d.0' % (i + 1)]), stage.layer(Wf['up%d.1' % (i + 1)])
+        F_.inc[0], F_.inc[1] = stage.layer(Wf['inc.0']), stage.layer(Wf['inc.1'])
         for i in range(6):
-            h, w = g2l_maps[i].hw
-            e = self.resize(k + 'encfix%d' % i, enc[i], (h, w))
-            if i > 0:
-                up_prev = self.resize(k + 'upprev%d' % i, prev, (h, w))
-                up_guide = self.resize(k + 'upguide%d' % i, guide[i - 1], (h, w))
-                e = self.conv(k + 'up%d.0' % i, Wf['up%d.0' % i], [e, up_prev, up_guide], act=ACT_RELU)
-                e = self.conv(k + 'up%d.1' % i, Wf['up%d.1' % i], [e], act=ACT_RELU)
-            gm = g2l_maps[i]
-            c = self.map(k + 'groi%d' % i, T, h, w, gm.C)
-            ops.roi_crop_zoom(gm.t, gm.C, boxes, h / self.P[0], c.t)
-            y = self.conv(k + 'cv%d.0' % i, Wf['cv%d.0' % i], [e, c], act=ACT_RELU)
-            prev = self.conv(k + 'cv%d.1' % i, Wf['cv%d.1' % i], [y], act=ACT_RELU)
-            outs.append(prev)
-            if taps is not None:
-                taps['fuse%d' % i] = prev.t.clone()
-        return self.metric_head('fus.head.', Wf['head'], self.hp['coarse'], self.bcfg['coarse'], outs[0], outs[1:5],
-                                outs[5], None, taps, depth_out=depth_out)
+            F_.cv[i][0], F_.cv[i][1] = stage.layer(Wf['cv%d.0' % i]), stage.layer(Wf['cv%d.1' % i])
+            L, g = Wf['g2l%d' % i], F_.g2l[i]
+            g.C, g.heads, g.depth = L['C'], L['heads'], len(L['blocks'])
+            g.ape, g.ape_rows = L['ape'].data_ptr(), L['ape'].shape[0]
+            g.nw, g.nb, g.ones = L['nw'].data_ptr(), L['nb'].data_ptr(), L['ones'].data_ptr()
+            blocks = (stage.PfG2LBlock * len(L['blocks']))()
+            for b, bw in enumerate(L['blocks']):
+                for k in ('n1w', 'n1b', 'n2w', 'n2b', 'table'):
+                    setattr(blocks[b], k, bw[k].data_ptr())
+                for k in ('qkv', 'proj', 'fc1', 'fc2'):
+                    setattr(blocks[b], k, stage.layer(bw[k]))
+            self._keep.append(blocks)
+            g.blocks = blocks
+        F_.head = self._c_head(Wf['head'], self.hp['coarse'], self.bcfg['coarse'], False)
+        return F_
+
+    # ------------------------------------------------------------------ workspaces (one arena per stage role)
+    def arena(self, name, nbytes):
+        """Persistent uint8 workspace `name` of at least nbytes (grown once to the largest request; growing bumps
+        `generation`, which invalidates graphs captured over the old addresses)."""
+        t = self.arenas.get(name)
+        if t is None or t.numel() < nbytes:
+            self.arenas[name] = t = torch.empty(int(nbytes) + 256, dtype=torch.uint8, device=self.dev)
+            self.generation += 1
+        return t
+
+    @staticmethod
+    def _view(arena, ptr, shape, dtype):
+        off = ptr - arena.data_ptr()
+        n = 1
+        for s_ in shape:
+            n *= s_
+        nbytes = n * torch.empty((), dtype=dtype).element_size()
+        assert 0 <= off and off + nbytes <= arena.numel()
+        return arena[off:off + nbytes].view(dtype).view(shape)
+
+    def _maps(self, arena, pf_maps):
+        return [Map(self._view(arena, m.ptr, (m.B, m.H, m.W, m.ld), BF16), m.C) for m in pf_maps]
+
+    def _tap_cb(self, arena, taps):
+        def cb(user, name, ptr, is_f32, rows, cols, ld):
+            t = self._view(arena, ptr, (rows, ld), F32 if is_f32 else BF16)
+            taps[name.decode()] = t[:, :cols].clone()
+        return cb
+
+    # ------------------------------------------------------------------ stages (sequenced inside libpf_b200)
+    def branch(self, which, images, taps=None, ws=None):
+        """images: planar fp32 [B,3,H,W] in [0,1] (un-normalised).  Returns (depth fp32 [B,H,W], feats[6] Maps
+        low->high: x_d0, r4, r3, r2, r1, out_conv) - views into the stage's workspace (`ws`: (arena, byte offset) to
+        place it; default = the branch's own arena)."""
+        from . import stage
+        cb = self.c_branch[which]
+        B = images.shape[0]
+        need = stage.branch_workspace_bytes(cb, B)
+        if ws is None:
+            arena, off = self.arena(which, need), 0
+        else:
+            arena, off = ws
+        assert images.dtype == F32 and images.is_contiguous() and off % 256 == 0 and off + need <= arena.numel()
+        tap = self._tap_cb(arena, taps) if taps is not None else None
+        out = stage.branch_forward(cb, images, B, arena.data_ptr() + off, need, tap)
+        H, W = self.P
+        depth = self._view(arena, out.depth, (B, H, W), F32)
+        feats = self._maps(arena, out.feats)
+        if taps is not None:
+            taps['rel'] = taps['rel'].view(B, H, W)
+            for k_ in list(taps):
+                if k_[0] == 'b' and k_[1:].isdigit():
+                    m = feats[1 + int(k_[1:])]
+                    taps[k_] = taps[k_].view(B, m.hw[0], m.hw[1], -1)
+        return depth, feats
+
+    def branch_bytes(self, which, B):
+        from . import stage
+        return stage.branch_workspace_bytes(self.c_branch[which], B)
+
+    @staticmethod
+    def _pf_maps(maps):
+        from . import stage
+        arr = (stage.PfMap * len(maps))()
+        for i, m in enumerate(maps):
+            arr[i].ptr, arr[i].C, arr[i].ld = m.t.data_ptr(), m.C, m.t.shape[-1]
+            arr[i].B, arr[i].H, arr[i].W = m.t.shape[0], m.t.shape[1], m.t.shape[2]
+        return arr
+
+    def g2l(self, coarse_feats):
+        """The six tile-invariant G2L maps of the whole-image coarse taps (computed once per image)."""
+        from . import stage
+        cm = self._pf_maps(coarse_feats)
+        need = stage.g2l_workspace_bytes(self.c_fusion, cm)
+        arena = self.arena('g2l', need)
+        out = stage.g2l_forward(self.c_fusion, cm, arena.data_ptr(), need)
+        return self._maps(arena, out)
+
+    def fusion_bytes(self, T, g2l_maps):
+        from . import stage
+        return stage.fusion_workspace_bytes(self.c_fusion, T, self._pf_maps(g2l_maps))
+
+    def fusion(self, crops, boxes, fine_depth, fine_feats, coarse_depth, coarse_feats, g2l_maps, taps=None,
+               depth_out=None, ws=None):
+        """crops planar fp32 [T,3,H,W]; boxes fp32 [T,4] (device, patch_process units); returns fp32 [T,H,W]."""
+        from . import stage
+        T = crops.shape[0]
+        H, W = self.P
+        gm = self._pf_maps(g2l_maps)
+        need = stage.fusion_workspace_bytes(self.c_fusion, T, gm)
+        if ws is None:
+            arena, off = self.arena('fusion', need), 0
+        else:
+            arena, off = ws
+        assert off % 256 == 0 and off + need <= arena.numel()
+        if depth_out is None:
+            depth_out = self.buf('fus.depth', (T, H, W), F32)
+        assert depth_out.dtype == F32 and depth_out.is_contiguous() and tuple(depth_out.shape) == (T, H, W)
+        for t_ in (crops, boxes, fine_depth, coarse_depth):
+            assert t_.dtype == F32 and t_.is_contiguous()
+        tap = self._tap_cb(arena, taps) if taps is not None else None
+        stage.fusion_forward(self.c_fusion, crops, boxes, T, fine_depth, self._pf_maps(fine_feats), coarse_depth,
+                             self._pf_maps(coarse_feats), gm, arena.data_ptr() + off, need, depth_out, tap)
+        if taps is not None:
+            for i in range(6):
+                m = g2l_maps[i]
+                taps['fuse%d' % i] = taps['fuse%d' % i].view(T, m.hw[0], m.hw[1], -1)
+        return depth_out

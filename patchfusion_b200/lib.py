@@ -10,7 +10,7 @@ import os
 import torch
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, 'libpf_b200.so')
+LIB_PATH = os.path.join(HERE, os.environ.get('PF_B200_LIBNAME', 'libpf_b200.so'))
 
 ACT_NONE, ACT_RELU, ACT_GELU, ACT_SOFTPLUS = 0, 1, 2, 3
 
@@ -43,10 +43,14 @@ class GemmDesc(C.Structure):
 _i, _f, _p, _ll = C.c_int32, C.c_float, C.c_void_p, C.c_int64
 # name -> argument types (all return int status), in the order of include/pf_b200.h
 SIGNATURES = {
+    'pf_profile_start': [_p],
+    'pf_profile_stop': [],
+    'pf_profile_get': [_i, _p, _p, _p, _p],
     'pf_gemm': [C.POINTER(GemmDesc), _p],
     'pf_pack_weight': [_p, _i, _i, _i, C.POINTER(C.c_int32), _i, _p, _p, _p],
     'pf_pack_weight_convT': [_p, _i, _i, _i, _p, _p],
     'pf_layernorm': [_p, _i, _p, _p, _f, _i, _i, _p, _i, _p],
+    'pf_layernorm_grouped': [_p, _i, _p, _p, _f, _i, _i, _i, _i, _i, _p, _i, _p],
     'pf_attention': [_p, _i, _p, _i, _i, _i, _i, _f, _p, _i, _p],
     'pf_patch_im2col': [_p, _i, _i, _i, _p, _i, _p],
     'pf_assemble_tokens': [_p, _p, _p, _i, _i, _i, _p, _p],
@@ -75,7 +79,8 @@ SIGNATURES = {
     'pf_stitch_reduce': [_p, _i, _ll, _p],
     'pf_stitch_resize': [_p, _p, _i, _i, _i, _i, _p, _p, _p],
 }
-EXPORTS = sorted(list(SIGNATURES) + ['pf_last_error', 'pf_version', 'pf_launch_count'])
+EXPORTS = sorted(list(SIGNATURES) + ['pf_last_error', 'pf_version', 'pf_launch_count', 'pf_branch_workspace_bytes', 'pf_branch_forward',
+                  'pf_g2l_workspace_bytes', 'pf_g2l_forward', 'pf_fusion_workspace_bytes', 'pf_fusion_forward'])
 
 _lib = None
 
@@ -117,42 +122,34 @@ def ptr(t):
 
 
 class Profiler:
-    """Optional per-launch CUDA-event timing (bench.py's roofline pass); off by default."""
+    """Per-launch CUDA-event timing inside the library (pf_profile_start/stop/get; bench.py's roofline pass): every
+    kernel libpf_b200 launches on the current stream between start() and stop() is recorded with its name, shape
+    label, algorithmic flops and duration.  While `lib.PROFILER` is set the model runs eagerly on one stream."""
 
     def __init__(self):
-        self.records = []
-        self.next_flops = 0.0
-        self.next_family = None
-        self.next_label = None
-        self.labels = []
+        self.records = []          # (kernel name, label, flops, ms)
 
-    def summary(self):
-        torch.cuda.synchronize()
-        out = {}
-        for fam, fl, e0, e1 in self.records:
-            d = out.setdefault(fam, dict(ms=0.0, flops=0.0, launches=0))
-            d['ms'] += e0.elapsed_time(e1)
-            d['flops'] += fl
-            d['launches'] += 1
-        return out
+    def start(self):
+        load().pf_profile_start(stream_ptr())
+
+    def stop(self):
+        h = load()
+        h.pf_profile_get.argtypes = [C.c_int32, C.POINTER(C.c_char_p), C.POINTER(C.c_char_p), C.POINTER(C.c_double),
+                                     C.POINTER(C.c_float)]
+        n = h.pf_profile_stop()
+        name, label, fl, ms = C.c_char_p(), C.c_char_p(), C.c_double(), C.c_float()
+        for i in range(n):
+            if h.pf_profile_get(i, C.byref(name), C.byref(label), C.byref(fl), C.byref(ms)) != 0:
+                raise PFError(h.pf_last_error().decode())
+            self.records.append((name.value.decode(), label.value.decode(), fl.value, ms.value))
+        return self.records
 
 
 PROFILER = None
 
 
 def call(name, *args):
-    if PROFILER is not None:
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        fl, PROFILER.next_flops = PROFILER.next_flops, 0.0
-        fam, PROFILER.next_family = PROFILER.next_family or name, None
-        lab, PROFILER.next_label = PROFILER.next_label or name, None
-        e0.record()
-        _call(name, *args)
-        e1.record()
-        PROFILER.records.append((fam, fl, e0, e1))
-        PROFILER.labels.append(lab)
-    else:
-        _call(name, *args)
+    _call(name, *args)
 
 
 def _call(name, *args):

@@ -271,14 +271,15 @@ class PatchFusion(ParamTree, PyTorchModelHubMixin):
         if not self.use_cuda_graphs or lib.PROFILER is not None:
             return fn()
         ent = self._graphs.get(key)
-        if ent is None:
+        eng = self._engine
+        if ent is None or ent[2] != eng.generation:     # workspaces were (re)allocated: old graphs point at freed memory
             fn()
             torch.cuda.synchronize()
             g = torch.cuda.CUDAGraph()
             n0 = lib.launch_count()
             with torch.cuda.graph(g):
                 fn()
-            self._graphs[key] = (g, lib.launch_count() - n0)
+            self._graphs[key] = (g, lib.launch_count() - n0, eng.generation)
             return None
         ent[0].replay()
         self.graph_launches += ent[1]          # kernels executed by the replay (for bench.py's gpu_launches)
@@ -299,14 +300,17 @@ class PatchFusion(ParamTree, PyTorchModelHubMixin):
         H, W, h, w, ph, pw = geom
         crops = eng.buf('tile.crops', (T, 3, ph, pw), torch.float32)
         ops.call('pf_crop_resize', img, H, W, raw, T, h, w, ph, pw, crops, ops.stream_ptr())
-        fd, ff = eng.branch('fine', crops)
-        return crops, fd, ff
+        # ONE arena for the tile stages, sized for the largest micro-batch: [fine branch | fusion]
+        nb = (eng.branch_bytes('fine', T) + 255) // 256 * 256
+        arena = eng.arena('tile', nb + eng.fusion_bytes(T, self._coarse[2]))
+        fd, ff = eng.branch('fine', crops, ws=(arena, 0))
+        return crops, fd, ff, (arena, nb)
 
     def _fusion_stage(self, eng, fine, boxes, out):
         """guided fusion of one micro-batch; the fused depth goes straight into its rows `out` of the prediction block."""
         cd, cf, g2l = self._coarse
-        crops, fd, ff = fine
-        eng.fusion(crops, boxes, fd, ff, cd, cf, g2l, depth_out=out)
+        crops, fd, ff, ws = fine
+        eng.fusion(crops, boxes, fd, ff, cd, cf, g2l, depth_out=out, ws=ws)
 
     def _image_stage(self, eng, lr, img, geom, sizes, io_raw, io_box, blk, with_coarse):
         """The static kernel sequence of one phase of one image on this rank: [coarse branch + G2L] and the

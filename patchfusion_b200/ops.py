@@ -136,15 +136,6 @@ def gemm(pw, srcs, out, *, image=None, ps_image=None, M=None, act=ACT_NONE, res1
         d.w2, d.b2 = w2.data_ptr(), (b2.data_ptr() if b2 is not None else None)
         d.n2, d.act2, d.skip_main = w2.shape[0], act2, 1 if skip_main else 0
         d.out3, d.out3_ld = tail_out.data_ptr(), tail_out.shape[-1]
-    if lib.PROFILER is not None:
-        n_true = pw.ps_cout * pw.ps * pw.ps if pw.ps > 1 else pw.N
-        lib.PROFILER.next_flops = 2.0 * rows * sum(cs) * pw.taps * n_true
-        if d.a_mode == 1 and pw.taps == 9 and tile is None:
-            lib.PROFILER.next_family = 'pf_conv3_halo'
-        lib.PROFILER.next_label = '%s rows%d C%s N%d%s%s' % (
-            'conv3x3' if pw.taps == 9 else ('conv1x1' if d.a_mode == 1 else ('convT' if pw.ps > 1 else 'linear')), rows,
-            '+'.join(str(c) for c in cs), n_true, ' act%d' % act if act else '',
-            ' gamma' if gamma is not None else (' vt' if vt is not None else (' tail%d' % d.n2 if tail is not None else '')))
     call('pf_gemm', C.byref(d), stream_ptr())
     return d
 
@@ -161,9 +152,6 @@ def layernorm(x, w, b, eps, out, rows=None, C_=None):
 
 
 def attention(qk, vt, B, seq, seq_pad, heads, scale, out):
-    if lib.PROFILER is not None:
-        lib.PROFILER.next_flops = 4.0 * B * heads * seq * seq * 64
-        lib.PROFILER.next_label = 'attention B%d h%d seq%d' % (B, heads, seq)
     call('pf_attention', qk, qk.shape[-1], vt, B, seq, seq_pad, heads, C.c_float(scale), out, out.shape[-1],
          stream_ptr())
 

@@ -73,9 +73,41 @@ def test_ctypes_signatures_match_header_arity():
     src = re.sub(r'/\*.*?\*/', '', open(HDR).read(), flags=re.S)
     protos = re.findall(r'\bint\s+(pf_[A-Za-z0-9_]+)\s*\(([^;{]*?)\)\s*;', src, flags=re.S)
     assert len(protos) >= 25
+    from patchfusion_b200 import stage
+    h = stage._bind()
     for name, args in protos:
         if name == 'pf_version':
             continue
         n = 0 if args.strip() == 'void' else len(args.split(','))
+        if name in stage.STAGE_EXPORTS:          # stage-level entry points are bound in patchfusion_b200/stage.py
+            assert n == len(getattr(h, name).argtypes), (name, n)
+            continue
         assert name in lib.SIGNATURES, name
         assert n == len(lib.SIGNATURES[name]), (name, n, len(lib.SIGNATURES[name]))
+
+
+def test_stage_struct_layouts(tmp_path):
+    """every struct of the stage-level ABI (pf_layer ... pf_fusion, pf_map, pf_branch_out): sizeof and the offset of
+    every field of the ctypes mirror equal the header's (checked with gcc)"""
+    import ctypes
+    from patchfusion_b200 import stage
+    prog = '#include <stdio.h>\n#include <stddef.h>\n#include "%s"\nint main(){' % HDR
+    for cname, cls in stage.STRUCTS.items():
+        prog += 'printf("%s sizeof %%zu\\n", sizeof(%s));' % (cname, cname)
+        for f in cls._fields_:
+            prog += 'printf("%s %s %%zu\\n", offsetof(%s, %s));' % (cname, f[0], cname, f[0])
+    prog += 'return 0;}'
+    c = tmp_path / 'lay.c'
+    c.write_text(prog)
+    exe = tmp_path / 'lay'
+    subprocess.check_call(['gcc', str(c), '-o', str(exe)])
+    n = 0
+    for line in subprocess.check_output([str(exe)], text=True).splitlines():
+        cname, field, v = line.split()
+        cls = stage.STRUCTS[cname]
+        if field == 'sizeof':
+            assert ctypes.sizeof(cls) == int(v), cname
+        else:
+            assert getattr(cls, field).offset == int(v), (cname, field)
+        n += 1
+    assert n > 100
