@@ -117,5 +117,99 @@ def main():
     print('wrote', os.path.join(GOLD, 'vits_case0.npz'))
 
 
+def main_default_init():
+    """Second reference-pinned fixture: weights drawn from the reference constructor's own distributions
+    (params.default_init_state_dict; per-tensor statistics checked against a freshly constructed reference model), the
+    reference's outputs for coarse / fine+fusion / m1 stored as strided samples (tests/golden/vits_default0.*)."""
+    from patchfusion_b200.params import default_init_state_dict
+    torch.set_num_threads(os.cpu_count())
+    case = dict(encoder='vits', seed=7, image_raw_shape=(1080, 1920), patch_split_num=(2, 2), process_num=2,
+                input_seed=1, sample_stride=4, init='default')
+    cfg = depth_anything_patchfusion(case['encoder'], image_raw_shape=case['image_raw_shape'],
+                                     patch_split_num=case['patch_split_num'])
+    ref = rh.build_reference(case['encoder'], cfg)
+    ref_sd = {k: v.clone() for k, v in ref.state_dict().items()}        # the reference's OWN default construction
+    sd = default_init_state_dict(cfg, seed=case['seed'])
+    assert list(sd) == list(ref_sd)
+    bad = []
+    for k, v in ref_sd.items():
+        if v.dtype != torch.float32 or v.numel() < 4096:
+            continue
+        a, b = v.double().std().item(), sd[k].double().std().item()
+        if abs(a - b) > 0.1 * max(a, 1e-12) + 1e-9:
+            bad.append((k, a, b))
+    assert not bad, bad[:5]
+    for k, v in ref_sd.items():                                           # small tensors: same constants / scale
+        if v.dtype == torch.float32 and v.numel() < 4096 and v.numel() > 1 and v.std() == 0:
+            assert torch.equal(v, sd[k]), k
+    print('default-init statistics match the reference constructor on', len(ref_sd), 'tensors')
+    print(ref.load_state_dict(sd, strict=True))
+    g = torch.Generator().manual_seed(case['input_seed'])
+    img = torch.rand(1, 3, *case['image_raw_shape'], generator=g)
+    orc = po.Oracle(sd, cfg)
+    lr = ref.resizer(img)
+    out, st = {}, case['sample_stride']
+    with torch.no_grad():
+        d_ref, f_ref = ref.coarse_forward(lr)
+        d_o, f_o = orc.coarse(lr)
+        assert (d_ref - d_o).abs().max() < 1e-5
+        out['coarse_depth'] = sample(d_ref, st)
+        for i, a in enumerate(f_ref):
+            out['coarse_feat%d_stats' % i] = stats(a)
+        random.seed(0)
+        y_ref, _ = ref(mode='infer', image_lr=lr, image_hr=img, cai_mode='m1', process_num=case['process_num'])
+        y_o = orc.infer(lr, img, cai_mode='m1', process_num=case['process_num'])
+        err = (y_ref - y_o).abs().max().item()
+        print('m1', tuple(y_ref.shape), 'max|ref-oracle| =', err, 'range', y_ref.min().item(), y_ref.max().item())
+        assert err < 1e-4
+        out['infer_m1'] = sample(y_ref, st)
+    np.savez_compressed(os.path.join(GOLD, 'vits_default0.npz'), **out)
+    json.dump({k: (list(v) if isinstance(v, tuple) else v) for k, v in case.items()},
+              open(os.path.join(GOLD, 'vits_default0.json'), 'w'))
+    print('wrote vits_default0')
+
+
+def main_vitl_tile():
+    """vitl-size fixture (SURVEY build-plan step 1): the reference's coarse depth and ONE fused 4K tile."""
+    torch.set_num_threads(os.cpu_count())
+    case = dict(encoder='vitl', seed=0, image_raw_shape=(2160, 3840), patch_split_num=(4, 4), input_seed=3,
+                sample_stride=4, tile=(540, 960))
+    cfg, sd, img = case_inputs(case)
+    ref = rh.build_reference(case['encoder'], cfg)
+    print(ref.load_state_dict(sd, strict=True))
+    orc = po.Oracle(sd, cfg)
+    lr = ref.resizer(img)
+    out, st = {}, case['sample_stride']
+    H, W = case['image_raw_shape']
+    h, w = H // 4, W // 4
+    y, x = case['tile']
+    P = cfg['patch_process_shape']
+    with torch.no_grad():
+        d_ref, f_ref = ref.coarse_forward(lr)
+        d_o, f_o = orc.coarse(lr)
+        print('coarse', (d_ref - d_o).abs().max().item())
+        assert (d_ref - d_o).abs().max() < 1e-4
+        out['coarse_depth'] = sample(d_ref, st)
+        fx, fy = 1 / W * P[1], 1 / H * P[0]
+        boxes = torch.tensor([[x, y, x + w, y + h]]).int() * torch.tensor([[fx, fy, fx, fy]])
+        bf = torch.cat([torch.zeros(1, 1), boxes], 1)
+        post = ref.coarse_postprocess_test(bboxs=None, bboxs_feat=bf, coarse_prediction=d_ref, coarse_features=f_ref)
+        crop = ref.resizer(img[:, :, y:y + h, x:x + w])
+        fd_ref, ff_ref = ref.fine_forward(crop)
+        fu_ref, _ = ref.fusion_forward(fd_ref, crop, f_ref, ff_ref, bf, **post)
+        g2l = po.g2l_all(sd, f_o, cfg['guided_fusion'])
+        tc = po.prepare_tile_cfg((H, W), (4, 4), P)
+        fu_o = orc.tiles(img, [(y, x)], d_o, f_o, g2l, 1, tc)
+        print('fusion', (fu_ref - fu_o).abs().max().item(), fu_ref.min().item(), fu_ref.max().item())
+        assert (fu_ref - fu_o).abs().max() < 1e-3 * fu_ref.abs().max()
+        out['fine_depth'] = sample(fd_ref, st)
+        out['fusion_depth'] = sample(fu_ref, st)
+    np.savez_compressed(os.path.join(GOLD, 'vitl_tile0.npz'), **out)
+    json.dump({k: (list(v) if isinstance(v, tuple) else v) for k, v in case.items()},
+              open(os.path.join(GOLD, 'vitl_tile0.json'), 'w'))
+    print('wrote vitl_tile0')
+
+
 if __name__ == '__main__':
-    main()
+    which = sys.argv[1] if len(sys.argv) > 1 else 'vits'
+    {'vits': main, 'default': main_default_init, 'vitl': main_vitl_tile}[which]()

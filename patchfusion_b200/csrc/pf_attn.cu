@@ -84,6 +84,24 @@ __device__ __forceinline__ void softmax_chunk(const uint32_t (&s)[32], uint64_t 
   }
 }
 
+// Debug timeline (build with -DPF_ATTN_TRACE, tools/attn_trace.py): CTA 0 records (role, tile, block, event, clock) tuples.
+#ifdef PF_ATTN_TRACE
+__device__ unsigned long long g_attn_trace[4096 * 2];
+__device__ unsigned int g_attn_trace_n;
+__device__ __forceinline__ void attn_trace(int role, int t, int j, int ev) {
+  if (blockIdx.x != 0) return;
+  unsigned int i = atomicAdd(&g_attn_trace_n, 1u);
+  if (i < 4096) {
+    g_attn_trace[2 * i] = (static_cast<unsigned long long>(role) << 48) | (static_cast<unsigned long long>(t) << 32) |
+                          (static_cast<unsigned long long>(j) << 16) | static_cast<unsigned long long>(ev);
+    g_attn_trace[2 * i + 1] = clock64();
+  }
+}
+#define ATTN_TRACE(role, t, j, ev) attn_trace(role, t, j, ev)
+#else
+#define ATTN_TRACE(role, t, j, ev)
+#endif
+
 struct AttnParams {
   CUtensorMap tmQK;   // 3-D {2*D, seq, B}, box {64, 128, 1}
   CUtensorMap tmVt;   // 2-D {seq_pad, B*heads*64}, box {64, 64}
@@ -188,6 +206,7 @@ __global__ void __launch_bounds__(kAttnThreads, 1) pf_attention_kernel(const __g
             if (t < nt) {
               mbar_wait(&s_free[t], sfree_ph[t] ^ 1); sfree_ph[t] ^= 1;
               tc_fence_after();
+              ATTN_TRACE(1, t, j, 0);
               const uint64_t dq = dq0 + t * (kTileBytes >> 4);
 #pragma unroll
               for (int k = 0; k < 4; ++k) umma_bf16(tmem_base + kColS + t * 128, dq + 2 * k, dk + 2 * k, idesc_s, k != 0);
@@ -222,6 +241,7 @@ __global__ void __launch_bounds__(kAttnThreads, 1) pf_attention_kernel(const __g
               mbar_wait(&p_full[t], pfull_ph[t]); pfull_ph[t] ^= 1;
               if (j == 0) { mbar_wait(&o_free[t], ofree_ph[t] ^ 1); ofree_ph[t] ^= 1; }
               tc_fence_after();
+              ATTN_TRACE(2, t, j, 0);
               const uint32_t tO = tmem_base + kColO + t * 64, tP = tmem_base + kColP + t * 64;
               for (int k = 0; k < nk; ++k)
                 umma_bf16_ts(tO, tP + k * 8, (k < 4 ? dv0 : dv1) + 2 * (k & 3), idesc_o, (j | k) != 0);
@@ -262,6 +282,7 @@ __global__ void __launch_bounds__(kAttnThreads, 1) pf_attention_kernel(const __g
           continue;
         }
         tc_fence_after();
+        if (q == 0 && lane == 0) ATTN_TRACE(0, t, j, 0);            // S ready
         bool waited = false;
         // O_t *= alpha, issued by the rows' own threads (rare: only when some row's max moved by > 2^8)
         auto rescale = [&](float m_new) {
@@ -289,6 +310,7 @@ __global__ void __launch_bounds__(kAttnThreads, 1) pf_attention_kernel(const __g
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&s_free[t]);              // QK^T of block j+1 may overwrite S now
+          if (q == 0 && lane == 0) ATTN_TRACE(0, t, j, 1);            // scores in registers
           float a0 = -INFINITY, a1 = -INFINITY, a2 = -INFINITY, a3 = -INFINITY;
 #pragma unroll
           for (int i = 0; i < 32; i += 2) {
@@ -309,10 +331,12 @@ __global__ void __launch_bounds__(kAttnThreads, 1) pf_attention_kernel(const __g
           softmax_chunk(s1, sc2, nm2, sum_a, sum_b, pk1);
           softmax_chunk(s2, sc2, nm2, sum_a, sum_b, pk2);
           softmax_chunk(s3, sc2, nm2, sum_a, sum_b, pk3);
+          if (q == 0 && lane == 0) ATTN_TRACE(0, t, j, 2);            // exps done
           if (j > 0 && !waited) {                              // PV of block j-1 has consumed the previous P
             mbar_wait(&o_done[t], odone_ph); odone_ph ^= 1;
             tc_fence_after();
           }
+          if (q == 0 && lane == 0) ATTN_TRACE(0, t, j, 3);            // PV(j-1) seen complete
           tmem_st16(tP, pk0);
           tmem_st16(tP + 16, pk1);
           tmem_st16(tP + 32, pk2);
@@ -363,6 +387,7 @@ __global__ void __launch_bounds__(kAttnThreads, 1) pf_attention_kernel(const __g
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&p_full[t]);
+        if (q == 0 && lane == 0) ATTN_TRACE(0, t, j, 4);              // P published
       }
       // ---- item epilogue: O / l -> bf16 -> global
       mbar_wait(&o_done[t], odone_ph); odone_ph ^= 1;
@@ -409,6 +434,17 @@ __global__ void __launch_bounds__(kAttnThreads, 1) pf_attention_kernel(const __g
 }  // namespace pf
 
 using namespace pf;
+
+#ifdef PF_ATTN_TRACE
+extern "C" int pf_attention_trace_read(unsigned long long* out, unsigned int* n) {
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(n, g_attn_trace_n, sizeof(unsigned int));
+  cudaMemcpyFromSymbol(out, g_attn_trace, sizeof(unsigned long long) * 4096 * 2);
+  unsigned int zero = 0;
+  cudaMemcpyToSymbol(g_attn_trace_n, &zero, sizeof(zero));
+  return 0;
+}
+#endif
 
 extern "C" int pf_attention(const void* qk, int32_t qk_ld, const void* vt, int32_t B, int32_t seq, int32_t seq_pad,
                             int32_t heads, float scale, void* out, int32_t out_ld, void* stream) {

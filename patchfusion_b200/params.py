@@ -324,3 +324,75 @@ def synthetic_state_dict(config, seed=0, dtype=torch.float32):
             raise AssertionError(key)
         sd[key] = t.to(dt if dt != torch.float32 else dtype)
     return sd
+
+
+def default_init_state_dict(config, seed=0):
+    """Seeded weights drawn from the distributions the REFERENCE's own constructor uses (no checkpoints are reachable
+    offline and the reference's exact RNG stream cannot be replayed on the GPU box, which has no reference tree):
+    DINOv2 `init_weights` (`vision_transformer.py:172-177,331-336`: trunc_normal(0.02) linears with zero bias,
+    pos_embed trunc_normal(0.02), cls N(0,1e-6), LayerScale 1.0 from `hubconf.py:38`), torch's default
+    kaiming_uniform(a=sqrt 5) = U(+-1/sqrt(fan_in)) for every other Conv2d / ConvTranspose2d / Linear and its bias,
+    identity LayerNorm / BatchNorm, trunc_normal(0.02) Swin position tables (`swin_layers.py:130,408`).
+    oracle/make_golden.py checks the per-tensor statistics against a freshly constructed reference model.  With
+    these weights the network output is nearly constant (every branch is far from trained), the regime the
+    variance-preserving `synthetic_state_dict` deliberately avoids."""
+    g = torch.Generator().manual_seed(seed)
+    layout = state_layout(config)
+    sd = OrderedDict()
+
+    def tn(shape, std):
+        return (torch.randn(shape, generator=g, dtype=torch.float32) * std).clamp_(-2.0, 2.0)   # trunc_normal_(a=-2, b=2)
+
+    def uni(shape, bound):
+        return (torch.rand(shape, generator=g, dtype=torch.float32) * 2 - 1) * bound
+
+    fan = {}
+    for key, (shape, dt, kind) in layout.items():
+        leaf = key.split('.')[-1]
+        vit = 'core.core.pretrained.' in key
+        if key.endswith('relative_position_index'):
+            t = relative_position_index()
+        elif leaf == 'k_idx':
+            t = torch.arange(shape[1]).view(shape)
+        elif leaf == 'K_minus_1':
+            t = torch.full(shape, float(layout[key.replace('K_minus_1', 'k_idx')][0][1] - 1))
+        elif leaf == 'num_batches_tracked':
+            t = torch.zeros((), dtype=torch.int64)
+        elif leaf == 'running_mean':
+            t = torch.zeros(shape)
+        elif leaf == 'running_var':
+            t = torch.ones(shape)
+        elif leaf == 'gamma':
+            t = torch.ones(shape)
+        elif leaf == 'cls_token':
+            t = torch.randn(shape, generator=g) * 1e-6
+        elif leaf == 'mask_token':
+            t = torch.zeros(shape)
+        elif leaf in ('pos_embed', 'absolute_pos_embed', 'relative_position_bias_table'):
+            t = tn(shape, 0.02)
+        elif leaf == 'weight' and len(shape) == 1:
+            t = torch.ones(shape)
+        elif leaf == 'weight':
+            if 'resize_layers.0' in key or 'resize_layers.1' in key:        # ConvTranspose2d weight (in, out, k, k)
+                fan_in = shape[1] * shape[2] * shape[3]
+            else:
+                fan_in = 1
+                for s_ in shape[1:]:
+                    fan_in *= s_
+            fan[key[:-len('weight')]] = fan_in
+            if vit and 'patch_embed' not in key:
+                t = tn(shape, 0.02)
+            else:
+                t = uni(shape, 1.0 / math.sqrt(fan_in))
+        elif leaf == 'bias':
+            pre = key[:-len('bias')]
+            if (pre + 'weight') in layout and len(layout[pre + 'weight'][0]) == 1:    # LayerNorm / BatchNorm
+                t = torch.zeros(shape)
+            elif vit and 'patch_embed' not in key:
+                t = torch.zeros(shape)
+            else:
+                t = uni(shape, 1.0 / math.sqrt(fan[pre]))
+        else:
+            raise AssertionError(key)
+        sd[key] = t.to(dt)
+    return sd

@@ -73,3 +73,22 @@ def test_metrics_oracle_matches_reference_fixture():
         got = mo.compute_metrics(gt, pred, c['lo'], c['hi'], edges)
         for k, v in ent['reference'].items():
             assert abs(float(got[k]) - v) <= 1e-6 * max(1.0, abs(v)), (c['name'], k)
+
+
+def test_oracle_matches_default_init_reference_fixture():
+    """the restatement against the real reference on weights drawn from the reference constructor's own distributions
+    (coarse branch only on CPU; the m1 canvas is checked on the GPU)"""
+    from oracle import pf_oracle as po
+    from patchfusion_b200.configs import depth_anything_patchfusion
+    from patchfusion_b200.params import default_init_state_dict
+    case = json.load(open(os.path.join(GOLD, 'vits_default0.json')))
+    gold = np.load(os.path.join(GOLD, 'vits_default0.npz'))
+    cfg = depth_anything_patchfusion(case['encoder'], image_raw_shape=case['image_raw_shape'],
+                                     patch_split_num=case['patch_split_num'])
+    sd = default_init_state_dict(cfg, seed=case['seed'])
+    img = torch.rand(1, 3, *case['image_raw_shape'], generator=torch.Generator().manual_seed(case['input_seed']))
+    orc = po.Oracle(sd, cfg)
+    with torch.no_grad():
+        d, _ = orc.coarse(orc.resizer(img))
+    st = case['sample_stride']
+    assert (d[..., ::st, ::st] - torch.tensor(gold['coarse_depth'])).abs().max().item() < 1e-5
