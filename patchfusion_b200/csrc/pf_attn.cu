@@ -8,14 +8,18 @@
 //                                                  with tcgen05.st - it never touches shared memory); V^T tiles come
 //                                                  from the transposed copy the qkv GEMM epilogue writes (K-major B).
 //   TMEM columns: S_0 0..127 | S_1 128..255 | O_0 256..319 | O_1 320..383 | P_0 384..447 | P_1 448..511
-// Warps 0-3 / 4-7: softmax of Q tile 0 / 1, ONE THREAD PER QUERY ROW (TMEM lane == row): the 128 scores of a KV block
-// are read from TMEM once into registers, the S buffer is handed back to the tensor core immediately (QK^T of block
-// j+1 overlaps softmax of block j), row max by 3-input FMNMX, exp2 on MUFU for most elements and on the FMA pipe
-// (Cody-Waite + cubic, packed FFMA2) for the rest - at head_dim 64 the MUFU pipe, not the tensor pipe, bounds
-// attention - packed FADD2 row sums, bf16 P back into TMEM.  O stays in TMEM across KV blocks; it is rescaled (by
-// the row's own thread) only when the running max moves by more than 2^8 (lazy rescale with a stale max, exact after
-// the final 1/l normalisation).  Warp 8 = TMA producer, warps 9 / 10 = single-thread QK^T / PV issuers.  K_j / V_j are shared by
-// the two Q tiles.  The last KV block (1037 = 8*128 + 13 keys) runs with N = 16 / K = 16 instead of a padded 128.
+// At head_dim 64 the softmax, not the tensor pipe, bounds attention (128 exps per row per 2x256-clk MMA), and what
+// bounded the softmax was LATENCY (TMEM load / store round trips, barrier hand-offs) with only two warps per
+// scheduler (profiles/r02_attention_*).  So the 16 softmax warps (4 per scheduler) STREAM the scores: two threads per
+// query row (TMEM lane == row; the warps w and w+4 of a quadrant own columns 0-63 / 64-127), 32 scores at a time
+// TMEM -> registers -> exp2 -> bf16 P -> TMEM, using the running maximum of the PREVIOUS blocks (known before the
+// scores arrive, so there is no max pass).  The block's own maximum is reduced on the side, exchanged between the two
+// half-row warps through shared memory, and only if some row's maximum moved by more than 2^8 is O rescaled (by the
+// rows' own threads) and the block redone with the new maximum - exact, and P never exceeds 2^8.  Block 0 (no
+// running maximum yet) takes the two passes.  exp2 runs on MUFU for most elements and on the FMA pipe (Cody-Waite +
+// cubic, packed FFMA2) for the rest; row sums are packed FADD2.  Warp 16 = TMA producer, warps 17 / 18 =
+// single-thread QK^T / PV issuers (separate, so a QK^T is never queued behind a wait for P).  K_j / V_j are shared
+// by the two Q tiles.  The last KV block (1037 = 8*128 + 13 keys) runs with N = 16 / K = 16, not a padded 128.
 #include <stdlib.h>
 
 #include "pf_common.cuh"
@@ -24,14 +28,16 @@
 namespace pf {
 
 constexpr int kQTile = 128, kKTile = 128, kHd = 64;
-constexpr int kAttnThreads = 352;                   // 8 softmax warps + TMA + QK^T issuer + PV issuer
+constexpr int kSoftmaxWarps = 16;
+constexpr int kAttnThreads = (kSoftmaxWarps + 3) * 32;   // + TMA producer + QK^T issuer + PV issuer
 constexpr int kKS = 3, kVS = 3;                      // K / V smem ring depths
 constexpr int kTileBytes = 16384;
 constexpr int kOffQ = 0;                             // 2 x [128 q][64]
 constexpr int kOffK = 2 * kTileBytes;                // kKS x [128 keys][64]
 constexpr int kOffV = kOffK + kKS * kTileBytes;      // kVS x 2 x [64 d][64 keys]
 constexpr int kOffBar = kOffV + kVS * kTileBytes;
-constexpr int kAttnSmem = 1024 + kOffBar + 512;
+constexpr int kOffXch = kOffBar + 512;                // fp32 [2 parities][2 tiles][2 halves][128 rows] block maxima + [2][2][128] row sums
+constexpr int kAttnSmem = 1024 + kOffXch + 6 * 1024;
 constexpr uint32_t kColS = 0, kColO = 256, kColP = 384;
 constexpr float kRescaleThreshold = 8.0f;            // log2 units: P stays below 2^8, far inside bf16 / fp32 range
 constexpr int kPolyPairs = 5;                        // of the 16 pairs per 32-score chunk, evaluated on the FMA pipe
@@ -88,18 +94,23 @@ __device__ __forceinline__ void softmax_chunk(const uint32_t (&s)[32], uint64_t 
 #ifdef PF_ATTN_TRACE
 __device__ unsigned long long g_attn_trace[4096 * 2];
 __device__ unsigned int g_attn_trace_n;
-__device__ __forceinline__ void attn_trace(int role, int t, int j, int ev) {
+// no atomics on the traced path: every recording thread owns a 1024-entry region (slot = role/tile) and a private
+// counter, so a trace point costs one clock read and two stores
+__device__ __forceinline__ void attn_trace(int role, int t, int j, int ev, unsigned int& cnt) {
   if (blockIdx.x != 0) return;
-  unsigned int i = atomicAdd(&g_attn_trace_n, 1u);
-  if (i < 4096) {
+  const unsigned int region = role == 0 ? t : (role + 1);
+  if (cnt < 1024) {
+    const unsigned int i = region * 1024 + cnt++;
     g_attn_trace[2 * i] = (static_cast<unsigned long long>(role) << 48) | (static_cast<unsigned long long>(t) << 32) |
-                          (static_cast<unsigned long long>(j) << 16) | static_cast<unsigned long long>(ev);
+                          (static_cast<unsigned long long>(j) << 16) | static_cast<unsigned long long>(ev) | (1ull << 63);
     g_attn_trace[2 * i + 1] = clock64();
   }
 }
-#define ATTN_TRACE(role, t, j, ev) attn_trace(role, t, j, ev)
+#define ATTN_TRACE(role, t, j, ev) attn_trace(role, t, j, ev, trace_cnt)
+#define ATTN_TRACE_DECL unsigned int trace_cnt = 0;
 #else
 #define ATTN_TRACE(role, t, j, ev)
+#define ATTN_TRACE_DECL
 #endif
 
 struct AttnParams {
@@ -135,28 +146,29 @@ __global__ void __launch_bounds__(kAttnThreads, 1) pf_attention_kernel(const __g
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int seq = P.seq;
   const int nkv = (seq + kKTile - 1) / kKTile;
+  ATTN_TRACE_DECL
   pdl_launch_dependents();
 
-  if (warp == 8 && lane == 0) {
+  if (warp == kSoftmaxWarps && lane == 0) {
     prefetch_tmap(&P.tmQK);
     prefetch_tmap(&P.tmVt);
     mbar_init(q_full, 1); mbar_init(q_empty, 1);
     for (int s = 0; s < kKS; ++s) { mbar_init(&k_full[s], 1); mbar_init(&k_empty[s], 1); }
     for (int s = 0; s < kVS; ++s) { mbar_init(&v_full[s], 1); mbar_init(&v_empty[s], 1); }
     for (int t = 0; t < 2; ++t) {
-      mbar_init(&s_full[t], 1); mbar_init(&s_free[t], 4); mbar_init(&p_full[t], 4);
-      mbar_init(&o_done[t], 1); mbar_init(&o_free[t], 4);
+      mbar_init(&s_full[t], 1); mbar_init(&s_free[t], 8); mbar_init(&p_full[t], 8);
+      mbar_init(&o_done[t], 1); mbar_init(&o_free[t], 8);
     }
     fence_barrier_init();
   }
-  if (warp == 9) tmem_alloc(tmem_slot, 512);
+  if (warp == kSoftmaxWarps + 1) tmem_alloc(tmem_slot, 512);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   pdl_wait();
 
-  if (warp == 8) {
+  if (warp == kSoftmaxWarps) {
     // ===================== TMA producer =====================
     if (lane == 0) {
       int ks = 0, vs = 0;
@@ -182,7 +194,7 @@ __global__ void __launch_bounds__(kAttnThreads, 1) pf_attention_kernel(const __g
         }
       }
     }
-  } else if (warp == 9) {
+  } else if (warp == kSoftmaxWarps + 1) {
     // ===================== QK^T issuer: S_t = Q_t K_j^T as soon as the softmax warps have taken S_t =====================
     // (a separate thread from the PV issuer, so a QK^T is never queued behind a wait for P)
     if (lane == 0) {
@@ -219,7 +231,7 @@ __global__ void __launch_bounds__(kAttnThreads, 1) pf_attention_kernel(const __g
         umma_commit(q_empty);                                  // every QK^T of the item is issued: Q may be replaced
       }
     }
-  } else if (warp == 10) {
+  } else if (warp == kSoftmaxWarps + 2) {
     // ===================== PV issuer: O_t += P_t V_j (A operand = P in TMEM) =====================
     if (lane == 0) {
       const uint32_t idesc_o = umma_idesc_bf16(128, kHd);
@@ -254,12 +266,16 @@ __global__ void __launch_bounds__(kAttnThreads, 1) pf_attention_kernel(const __g
       }
     }
   } else {
-    // ===================== softmax warps: one thread per query row =====================
-    const int t = warp >> 2, q = warp & 3;
+    // ===================== softmax warps: two threads per query row, scores streamed 32 at a time =====================
+    const int t = warp >> 3, hh = (warp >> 2) & 1, q = warp & 3;
+    const int r = q * 32 + lane;                               // query row of the tile (== TMEM lane)
     const uint32_t lane_sel = static_cast<uint32_t>(q * 32) << 16;
-    const uint32_t tS = tmem_base + lane_sel + kColS + t * 128;
-    const uint32_t tO = tmem_base + lane_sel + kColO + t * 64;
-    const uint32_t tP = tmem_base + lane_sel + kColP + t * 64;
+    const uint32_t tS = tmem_base + lane_sel + kColS + t * 128 + hh * 64;    // my 64 score columns
+    const uint32_t tO = tmem_base + lane_sel + kColO + t * 64 + hh * 32;     // my 32 output columns
+    const uint32_t tP = tmem_base + lane_sel + kColP + t * 64 + hh * 32;     // my 32 packed-P columns (64 keys)
+    float* xch = reinterpret_cast<float*>(smem + kOffXch);                   // [parity][tile][half][128]
+    float* xsum = xch + 2 * 2 * 2 * 128;                                     // [tile][half][128]
+    const int pair_bar = 1 + t * 4 + q;                        // named barrier of the two warps sharing these rows
     const float scale = P.scale_log2;
     uint32_t sfull_ph = 0, odone_ph = 0;
     for (int item = blockIdx.x; item < P.n_items; item += gridDim.x) {
@@ -267,165 +283,174 @@ __global__ void __launch_bounds__(kAttnThreads, 1) pf_attention_kernel(const __g
       const int h = bh % P.heads, b = bh / P.heads;
       const int row0 = pair * 2 * kQTile + t * kQTile;
       if (row0 >= seq) continue;                               // this tile holds no queries: no barrier traffic at all
-      const bool warp_active = row0 + q * 32 < seq;            // warp-uniform
-      const int tok = row0 + q * 32 + lane;
+      const bool warp_active = row0 + q * 32 < seq;            // warp-uniform, same for both half-row warps
+      const int tok = row0 + r;
+      if (!warp_active) {
+        // rows beyond the sequence: keep the tile's barrier protocol, skip the math
+        for (int j = 0; j < nkv; ++j) {
+          mbar_wait(&s_full[t], sfull_ph); sfull_ph ^= 1;
+          if (j > 0) { mbar_wait(&o_done[t], odone_ph); odone_ph ^= 1; }
+          __syncwarp();
+          if (lane == 0) { mbar_arrive(&s_free[t]); mbar_arrive(&p_full[t]); }
+        }
+        mbar_wait(&o_done[t], odone_ph); odone_ph ^= 1;
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&o_free[t]);
+        continue;
+      }
       float m_run = -INFINITY, l_run = 0.0f;
       for (int j = 0; j < nkv; ++j) {
         const int kv_len = min(kKTile, seq - j * kKTile);
+        const int my_valid = max(0, min(64, kv_len - hh * 64));      // keys of this block among my 64 columns
+        float* xm = xch + (((j & 1) * 2 + t) * 2) * 128;             // [half][128] of this parity / tile
         mbar_wait(&s_full[t], sfull_ph); sfull_ph ^= 1;
-        if (!warp_active) {                                    // keep the barrier protocol, skip the math
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&s_free[t]);
-          if (j > 0) { mbar_wait(&o_done[t], odone_ph); odone_ph ^= 1; }
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&p_full[t]);
-          continue;
-        }
         tc_fence_after();
-        if (q == 0 && lane == 0) ATTN_TRACE(0, t, j, 0);            // S ready
-        bool waited = false;
-        // O_t *= alpha, issued by the rows' own threads (rare: only when some row's max moved by > 2^8)
-        auto rescale = [&](float m_new) {
-          const float alpha = ex2_approx(m_run - m_new);
-          m_run = m_new;
-          l_run *= alpha;
-          mbar_wait(&o_done[t], odone_ph); odone_ph ^= 1;      // PV of block j-1 must have landed in O
-          waited = true;
-          tc_fence_after();
-#pragma unroll 1
-          for (int part = 0; part < 4; ++part) {               // 16 columns at a time: the 128 scores stay in registers
-            uint32_t o[16];
-            tmem_ld16(tO + part * 16, o);
-            tmem_ld_wait();
-#pragma unroll
-            for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-            tmem_st16(tO + part * 16, o);
-          }
-          tmem_st_wait();
+        if (q == 0 && lane == 0 && hh == 0) ATTN_TRACE(0, t, j, 0);
+        bool pv_waited = j == 0;                               // PV of block j-1 must finish before P / O are touched
+        auto wait_pv = [&]() {
+          if (!pv_waited) { mbar_wait(&o_done[t], odone_ph); odone_ph ^= 1; tc_fence_after(); pv_waited = true; }
         };
-        if (kv_len == kKTile) {
-          uint32_t s0[32], s1[32], s2[32], s3[32];
-          tmem_ld32(tS, s0); tmem_ld32(tS + 32, s1); tmem_ld32(tS + 64, s2); tmem_ld32(tS + 96, s3);
-          tmem_ld_wait();
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&s_free[t]);              // QK^T of block j+1 may overwrite S now
-          if (q == 0 && lane == 0) ATTN_TRACE(0, t, j, 1);            // scores in registers
-          float a0 = -INFINITY, a1 = -INFINITY, a2 = -INFINITY, a3 = -INFINITY;
+        // exchange a per-row value with the warp that owns the other 64 columns of the same rows
+        auto pair_max = [&](float v) -> float {
+          xm[hh * 128 + r] = v;
+          asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
+          return fmaxf(v, xm[(hh ^ 1) * 128 + r]);
+        };
+        // raw (unscaled) maximum over my valid columns: block 0 only (no running maximum yet)
+        auto max_pass = [&]() -> float {
+          float mx = -INFINITY;
 #pragma unroll
-          for (int i = 0; i < 32; i += 2) {
-            a0 = max3(a0, __uint_as_float(s0[i]), __uint_as_float(s0[i + 1]));
-            a1 = max3(a1, __uint_as_float(s1[i]), __uint_as_float(s1[i + 1]));
-            a2 = max3(a2, __uint_as_float(s2[i]), __uint_as_float(s2[i + 1]));
-            a3 = max3(a3, __uint_as_float(s3[i]), __uint_as_float(s3[i + 1]));
+          for (int c = 0; c < 2; ++c) {
+            if (c * 32 < my_valid) {
+              uint32_t v[32];
+              tmem_ld32(tS + c * 32, v);
+              tmem_ld_wait();
+              if (my_valid - c * 32 >= 32) {
+                float a0 = -INFINITY, a1 = -INFINITY;
+#pragma unroll
+                for (int i = 0; i < 32; i += 4) {
+                  a0 = max3(a0, __uint_as_float(v[i]), __uint_as_float(v[i + 1]));
+                  a1 = max3(a1, __uint_as_float(v[i + 2]), __uint_as_float(v[i + 3]));
+                }
+                mx = max3(mx, a0, a1);
+              } else {
+#pragma unroll
+                for (int i = 0; i < 32; ++i)
+                  if (c * 32 + i < my_valid) mx = fmaxf(mx, __uint_as_float(v[i]));
+              }
+            }
           }
-          const float m_new = fmaxf(m_run, fmaxf(fmaxf(a0, a1), fmaxf(a2, a3)) * scale);
-          if (j == 0) m_run = m_new;
-          else if (__any_sync(0xffffffffu, m_new - m_run > kRescaleThreshold)) rescale(m_new);
-          const uint64_t sc2 = pack2f(scale, scale), nm2 = pack2f(-m_run, -m_run);
+          return mx;
+        };
+        // P = exp2(S * scale - m) for my 64 columns, 32 at a time; returns the block's row sum and raw maximum
+        auto stream_pass = [&](float m, float& blk_sum, float& raw_max) {
+          const uint64_t sc2 = pack2f(scale, scale), nm2 = pack2f(-m, -m);
           uint64_t sum_a = 0, sum_b = 0;                       // bit pattern of (+0.0f, +0.0f)
-          // all 128 probabilities first (the scores die chunk by chunk), THEN the wait for PV of block j-1 (which
-          // has had the whole softmax to complete) and the four TMEM stores back to back
-          uint32_t pk0[16], pk1[16], pk2[16], pk3[16];
-          softmax_chunk(s0, sc2, nm2, sum_a, sum_b, pk0);
-          softmax_chunk(s1, sc2, nm2, sum_a, sum_b, pk1);
-          softmax_chunk(s2, sc2, nm2, sum_a, sum_b, pk2);
-          softmax_chunk(s3, sc2, nm2, sum_a, sum_b, pk3);
-          if (q == 0 && lane == 0) ATTN_TRACE(0, t, j, 2);            // exps done
-          if (j > 0 && !waited) {                              // PV of block j-1 has consumed the previous P
-            mbar_wait(&o_done[t], odone_ph); odone_ph ^= 1;
-            tc_fence_after();
+          float ls = 0.0f, mx = -INFINITY;
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            uint32_t pk[16];
+            const int vc = my_valid - c * 32;                  // warp-uniform
+            if (vc >= 32) {
+              uint32_t v[32];
+              tmem_ld32(tS + c * 32, v);
+              tmem_ld_wait();
+              float a0 = -INFINITY, a1 = -INFINITY;
+#pragma unroll
+              for (int i = 0; i < 32; i += 4) {
+                a0 = max3(a0, __uint_as_float(v[i]), __uint_as_float(v[i + 1]));
+                a1 = max3(a1, __uint_as_float(v[i + 2]), __uint_as_float(v[i + 3]));
+              }
+              mx = max3(mx, a0, a1);
+              softmax_chunk(v, sc2, nm2, sum_a, sum_b, pk);
+            } else if (vc > 0) {
+              uint32_t v[32];
+              tmem_ld32(tS + c * 32, v);
+              tmem_ld_wait();
+#pragma unroll
+              for (int i = 0; i < 16; ++i) {
+                const bool k0 = 2 * i < vc, k1 = 2 * i + 1 < vc;
+                const float e0 = k0 ? ex2_approx(fmaf(__uint_as_float(v[2 * i]), scale, -m)) : 0.0f;
+                const float e1 = k1 ? ex2_approx(fmaf(__uint_as_float(v[2 * i + 1]), scale, -m)) : 0.0f;
+                if (k0) mx = fmaxf(mx, __uint_as_float(v[2 * i]));
+                if (k1) mx = fmaxf(mx, __uint_as_float(v[2 * i + 1]));
+                ls += e0 + e1;
+                pk[i] = pack_bf16(e0, e1);
+              }
+            } else {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) pk[i] = 0u;
+            }
+            if (c == 0) wait_pv();
+            tmem_st16(tP + c * 16, pk);
           }
-          if (q == 0 && lane == 0) ATTN_TRACE(0, t, j, 3);            // PV(j-1) seen complete
-          tmem_st16(tP, pk0);
-          tmem_st16(tP + 16, pk1);
-          tmem_st16(tP + 32, pk2);
-          tmem_st16(tP + 48, pk3);
           float x0, x1, y0, y1;
           unpack2f(sum_a, x0, x1);
           unpack2f(sum_b, y0, y1);
-          l_run += (x0 + x1) + (y0 + y1);
+          blk_sum = ls + ((x0 + x1) + (y0 + y1));
+          raw_max = mx;
+        };
+        float blk_sum, raw_max;
+        if (j == 0) {
+          m_run = pair_max(max_pass()) * scale;                // the row has at least one key: finite
+          stream_pass(m_run, blk_sum, raw_max);
         } else {
-          // ragged last block: only the chunks that hold keys, masked; two passes over TMEM (cheap: <= 1/8 of the row)
-          const int nch = (kv_len + 31) >> 5;
-          uint32_t v[32];
-          float mx = -INFINITY;
-          for (int c = 0; c < nch; ++c) {
-            tmem_ld32(tS + c * 32, v);
+          stream_pass(m_run, blk_sum, raw_max);                // with the STALE maximum: no max pass on the critical path
+          const float m_blk = pair_max(raw_max) * scale;       // -inf * scale = -inf when I own no valid column
+          if (__any_sync(0xffffffffu, m_blk - m_run > kRescaleThreshold)) {
+            // some row's maximum moved by more than 2^8 (rare): rescale O (PV of block j-1 is complete, wait_pv ran),
+            // then redo the block with the new maximum.  Both half-row warps take this branch together.
+            const float m_new = fmaxf(m_run, m_blk);
+            const float alpha = ex2_approx(m_run - m_new);
+            m_run = m_new;
+            l_run *= alpha;
+            uint32_t o[32];
+            tmem_ld32(tO, o);
             tmem_ld_wait();
 #pragma unroll
-            for (int i = 0; i < 32; ++i)
-              if (c * 32 + i < kv_len) mx = fmaxf(mx, __uint_as_float(v[i]));
+            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+            tmem_st32(tO, o);
+            stream_pass(m_run, blk_sum, raw_max);
           }
-          const float m_new = fmaxf(m_run, mx * scale);
-          if (j == 0) m_run = m_new;
-          else if (__any_sync(0xffffffffu, m_new - m_run > kRescaleThreshold)) rescale(m_new);
-          float ls = 0.0f;
-          for (int c = 0; c < nch; ++c) {
-            tmem_ld32(tS + c * 32, v);
-            tmem_ld_wait();
-            uint32_t pk[16];
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              const float e0 = (c * 32 + 2 * i < kv_len) ? ex2_approx(fmaf(__uint_as_float(v[2 * i]), scale, -m_run)) : 0.0f;
-              const float e1 = (c * 32 + 2 * i + 1 < kv_len) ? ex2_approx(fmaf(__uint_as_float(v[2 * i + 1]), scale, -m_run)) : 0.0f;
-              ls += e0 + e1;
-              pk[i] = pack_bf16(e0, e1);
-            }
-            if (c == 0 && j > 0 && !waited) {
-              mbar_wait(&o_done[t], odone_ph); odone_ph ^= 1;
-              tc_fence_after();
-            }
-            tmem_st16(tP + c * 16, pk);
-          }
-          l_run += ls;
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&s_free[t]);
         }
+        l_run += blk_sum;
         tmem_st_wait();
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&p_full[t]);
-        if (q == 0 && lane == 0) ATTN_TRACE(0, t, j, 4);              // P published
+        if (lane == 0) { mbar_arrive(&s_free[t]); mbar_arrive(&p_full[t]); }
+        if (q == 0 && lane == 0 && hh == 0) ATTN_TRACE(0, t, j, 4);
       }
-      // ---- item epilogue: O / l -> bf16 -> global
+      // ---- item epilogue: combine the two half-row sums, O / l -> bf16 -> global
+      float* xs = xsum + (t * 2) * 128;
+      xs[hh * 128 + r] = l_run;
       mbar_wait(&o_done[t], odone_ph); odone_ph ^= 1;
-      if (warp_active) {
-        tc_fence_after();
-        uint32_t o0[32], o1[32];
-        tmem_ld32(tO, o0);
-        tmem_ld32(tO + 32, o1);
-        tmem_ld_wait();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&o_free[t]);                // PV of the next item may overwrite O
-        if (tok < seq) {
-          const float inv = 1.0f / l_run;
-          __nv_bfloat16* op = P.out + (static_cast<long long>(b) * seq + tok) * P.out_ld + h * kHd;
+      tc_fence_after();
+      uint32_t o[32];
+      tmem_ld32(tO, o);
+      tmem_ld_wait();
+      tc_fence_before();
+      asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
+      const float l_tot = l_run + xs[(hh ^ 1) * 128 + r];
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&o_free[t]);                  // PV of the next item may overwrite O
+      if (tok < seq) {
+        const float inv = 1.0f / l_tot;
+        __nv_bfloat16* op = P.out + (static_cast<long long>(b) * seq + tok) * P.out_ld + h * kHd + hh * 32;
 #pragma unroll
-          for (int i = 0; i < 32; i += 8) {
-            *reinterpret_cast<uint4*>(op + i) = make_uint4(
-                pack_bf16(__uint_as_float(o0[i]) * inv, __uint_as_float(o0[i + 1]) * inv),
-                pack_bf16(__uint_as_float(o0[i + 2]) * inv, __uint_as_float(o0[i + 3]) * inv),
-                pack_bf16(__uint_as_float(o0[i + 4]) * inv, __uint_as_float(o0[i + 5]) * inv),
-                pack_bf16(__uint_as_float(o0[i + 6]) * inv, __uint_as_float(o0[i + 7]) * inv));
-            *reinterpret_cast<uint4*>(op + 32 + i) = make_uint4(
-                pack_bf16(__uint_as_float(o1[i]) * inv, __uint_as_float(o1[i + 1]) * inv),
-                pack_bf16(__uint_as_float(o1[i + 2]) * inv, __uint_as_float(o1[i + 3]) * inv),
-                pack_bf16(__uint_as_float(o1[i + 4]) * inv, __uint_as_float(o1[i + 5]) * inv),
-                pack_bf16(__uint_as_float(o1[i + 6]) * inv, __uint_as_float(o1[i + 7]) * inv));
-          }
+        for (int i = 0; i < 32; i += 8) {
+          *reinterpret_cast<uint4*>(op + i) = make_uint4(
+              pack_bf16(__uint_as_float(o[i]) * inv, __uint_as_float(o[i + 1]) * inv),
+              pack_bf16(__uint_as_float(o[i + 2]) * inv, __uint_as_float(o[i + 3]) * inv),
+              pack_bf16(__uint_as_float(o[i + 4]) * inv, __uint_as_float(o[i + 5]) * inv),
+              pack_bf16(__uint_as_float(o[i + 6]) * inv, __uint_as_float(o[i + 7]) * inv));
         }
-      } else {
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&o_free[t]);
       }
+      // the pair barrier at the top of the next item's first exchange orders the xsum reads before its next write
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 9) {
+  if (warp == kSoftmaxWarps + 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
   }
@@ -438,10 +463,8 @@ using namespace pf;
 #ifdef PF_ATTN_TRACE
 extern "C" int pf_attention_trace_read(unsigned long long* out, unsigned int* n) {
   cudaDeviceSynchronize();
-  cudaMemcpyFromSymbol(n, g_attn_trace_n, sizeof(unsigned int));
+  *n = 4096;
   cudaMemcpyFromSymbol(out, g_attn_trace, sizeof(unsigned long long) * 4096 * 2);
-  unsigned int zero = 0;
-  cudaMemcpyToSymbol(g_attn_trace_n, &zero, sizeof(zero));
   return 0;
 }
 #endif

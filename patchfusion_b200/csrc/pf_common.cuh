@@ -55,11 +55,25 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// Non-blocking probe of a phase (the result is used many instructions later: its latency hides under other work).
+__device__ __forceinline__ bool mbar_test_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P1;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
+      "selp.b32 %0, 1, 0, P1;\n\t"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
 // Bounded wait: a protocol bug traps (surfacing as a launch error) instead of hanging the GPU box.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins > (1u << 24)) { __trap(); }
+    if (++spins > (1u << 20)) { __trap(); }
   }
 }
 
@@ -242,6 +256,34 @@ __device__ __forceinline__ uint64_t sub2(uint64_t a, uint64_t b) {
   uint64_t d;
   asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
   return d;
+}
+__device__ __forceinline__ uint64_t mul2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+// exact-erf GELU of two values with packed FFMA2 / FMUL2 (same Abramowitz-Stegun 7.1.26 form as gelu_erf):
+// gelu(x) = 0.5 x + 0.5 |x| erf(|x| / sqrt 2) - ~9.5 issue slots per element instead of ~18.
+__device__ __forceinline__ void gelu_erf2(float& x0, float& x1) {
+  const uint64_t x = pack2f(x0, x1);
+  const uint64_t ax = pack2f(fabsf(x0), fabsf(x1));
+  const uint64_t u = mul2(ax, pack2f(0.70710678118654752440f, 0.70710678118654752440f));
+  float d0, d1;
+  unpack2f(fma2(u, pack2f(0.3275911f, 0.3275911f), pack2f(1.0f, 1.0f)), d0, d1);
+  const uint64_t t = pack2f(__fdividef(1.0f, d0), __fdividef(1.0f, d1));
+  uint64_t p = fma2(t, pack2f(1.061405429f, 1.061405429f), pack2f(-1.453152027f, -1.453152027f));
+  p = fma2(t, p, pack2f(1.421413741f, 1.421413741f));
+  p = fma2(t, p, pack2f(-0.284496736f, -0.284496736f));
+  p = fma2(t, p, pack2f(0.254829592f, 0.254829592f));
+  p = mul2(p, t);
+  float a0, a1;
+  unpack2f(mul2(mul2(u, u), pack2f(-1.4426950408889634f, -1.4426950408889634f)), a0, a1);   // -u^2 * log2(e)
+  float e0, e1;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(a0));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(a1));
+  const uint64_t erf = fma2(p, pack2f(-e0, -e1), pack2f(1.0f, 1.0f));                          // 1 - p t exp(-u^2)
+  const uint64_t h = pack2f(0.5f, 0.5f);
+  unpack2f(fma2(mul2(ax, h), erf, mul2(x, h)), x0, x1);
 }
 __device__ __forceinline__ float max3(float a, float b, float c) {
   float d;

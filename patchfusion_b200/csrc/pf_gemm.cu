@@ -92,8 +92,13 @@ __device__ __forceinline__ void epilogue_chunk(const GemmDesc& d, float (&f)[W],
 #pragma unroll
     for (int j = 0; j < W; ++j) f[j] = fmaxf(f[j], 0.0f);
   } else if (d.act == PF_ACT_GELU) {
+    if (FULL) {
 #pragma unroll
-    for (int j = 0; j < W; ++j) if (FULL || j < nvalid) f[j] = gelu_erf(f[j]);
+      for (int j = 0; j < W; j += 2) gelu_erf2(f[j], f[j + 1]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < W; ++j) if (j < nvalid) f[j] = gelu_erf(f[j]);
+    }
   } else if (d.act == PF_ACT_SOFTPLUS) {
 #pragma unroll
     for (int j = 0; j < W; ++j) if (FULL || j < nvalid) f[j] = softplus(f[j]);
