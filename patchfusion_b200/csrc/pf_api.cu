@@ -373,7 +373,14 @@ int pf_gemm(pf_gemm_desc* u, void* stream) {
   d.vt = static_cast<__nv_bfloat16*>(u->vt);
   d.vt_col0 = u->vt_col0; d.vt_seq = u->vt_seq; d.vt_seq_pad = u->vt_seq_pad; d.vt_dim = u->vt_dim;
   if (d.vt && (d.vt_col0 % bn) != 0) return set_error("pf_gemm: vt_col0 must be a multiple of block_n");
-  return gemm_launch(d, tmA, tmB, static_cast<cudaStream_t>(stream));
+  // Linear layers with several m-tiles per n-tile are L2 -> SM bandwidth bound: pairs of CTAs share the weight tile by
+  // TMA multicast (PF_B200_NO_MULTICAST=1 disables).  Needs an even split of the n-tile into 1024-B aligned halves.
+  static const bool no_mc = getenv("PF_B200_NO_MULTICAST") != nullptr;
+  const bool mc = !no_mc && !halo && u->a_mode == 0 && d.ps == 1 && bn % 16 == 0 && d.m_tiles >= 4 &&
+                  static_cast<long long>(d.m_tiles) * d.n_tiles >= 148;
+  CUtensorMap tmBh;
+  if (mc && tmap_2d_bf16(&tmBh, u->w_ptr, u->Ktot, n_pad, u->Ktot, 64, bn / 2)) return 1;
+  return gemm_launch(d, tmA, tmB, mc ? &tmBh : nullptr, static_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"

@@ -32,6 +32,7 @@ constexpr int kGemmThreads = 64 + kEpiWarps * 32;  // + TMA producer warp + MMA/
 struct GemmKernelParams {
   CUtensorMap tmA[3];
   CUtensorMap tmB;
+  CUtensorMap tmBh;     // multicast variant: box of block_n / 2 weight rows (each CTA of the pair fetches one half)
   GemmDesc d;
   int stages;
   int total_tiles;
@@ -241,15 +242,35 @@ __device__ __forceinline__ void epilogue_row(const GemmDesc& d, uint32_t taddr, 
 }
 
 // Epilogue warps (4 warps, TMEM lane quadrant = warp & 3): drain accumulator stage `acc` of each tile this CTA owns.
-__device__ __forceinline__ void epilogue_loop(const GemmDesc& d, int total_tiles, uint64_t* tmem_full,
+// Tile schedule.  Plain: CTA b takes tiles b, b + grid, ...  Multicast pairs (MC): cluster c takes tile PAIRS c, c + clusters, ...
+// where pair p = (m-tile pair p / n_tiles, n-tile p % n_tiles) and the CTA of cluster rank r owns m-tile 2 * mp + r
+// (an odd last m-tile pairs with an all-out-of-range one: TMA zero-fills it, the epilogue drops its rows).
+struct TileIter {
+  int first, step, count, rank, n_tiles;
+  bool mc;
+  __device__ __forceinline__ int tile(int i) const {
+    if (!mc) return i;
+    const int nt = i % n_tiles, mp = i / n_tiles;
+    return (2 * mp + rank) * n_tiles + nt;
+  }
+};
+__device__ __forceinline__ TileIter make_iter(const GemmDesc& d, int total_tiles, bool mc) {
+  TileIter it;
+  it.mc = mc; it.n_tiles = d.n_tiles;
+  if (!mc) { it.first = blockIdx.x; it.step = gridDim.x; it.count = total_tiles; it.rank = 0; }
+  else { it.first = blockIdx.x >> 1; it.step = gridDim.x >> 1; it.count = ((d.m_tiles + 1) >> 1) * d.n_tiles; it.rank = cluster_ctarank(); }
+  return it;
+}
+
+__device__ __forceinline__ void epilogue_loop(const GemmDesc& d, const TileIter& it, uint64_t* tmem_full,
                                               uint64_t* tmem_empty, uint32_t tmem_base, int warp, int lane,
                                               float* tail_smem) {
   const int q = warp & 3;                 // TMEM lane quadrant this warp may access
   const int half = (warp - 2) >> 2;       // which of the quadrant's two warps: takes every other 32-column chunk
   const int r = q * 32 + lane;            // accumulator row owned by this thread
   int acc = 0; uint32_t acc_phase = 0;
-  for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-    TileCoord c = decode_tile(d, t);
+  for (int ti = it.first; ti < it.count; ti += it.step) {
+    TileCoord c = decode_tile(d, it.tile(ti));
     // ---- row mapping
     bool row_ok;
     long long orow;       // output row (pixel / token) index
@@ -319,6 +340,10 @@ __device__ __forceinline__ void epilogue_loop(const GemmDesc& d, int total_tiles
   }
 }
 
+// MC = true: launched as clusters of 2 CTAs that take two m-tiles of the SAME n-tile; each CTA fetches half of the
+// weight tile and multicasts it into both CTAs' shared memory (the linear layers are bound by L2 -> SM bandwidth:
+// A 16 KB + B 32 KB per 512 MMA clocks is ~94 B/clk/SM against a chip-wide ~43 B/clk/SM; halving B cuts it by a third).
+template <bool MC>
 __global__ void __launch_bounds__(kGemmThreads, 1) pf_gemm_kernel(const __grid_constant__ GemmKernelParams P) {
   extern __shared__ uint8_t smem_raw[];
   const GemmDesc& d = P.d;
@@ -341,23 +366,26 @@ __global__ void __launch_bounds__(kGemmThreads, 1) pf_gemm_kernel(const __grid_c
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < d.num_src; ++s) prefetch_tmap(&P.tmA[s]);
     prefetch_tmap(&P.tmB);
-    for (int s = 0; s < stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    // a multicast stage is refilled only after BOTH CTAs' MMAs released it: two arrivals per phase
+    for (int s = 0; s < stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], MC ? 2 : 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], kEpiWarps * 32); }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, 512);
   tc_fence_before();
   __syncthreads();
+  if (MC) cluster_sync_all();       // the peer's barriers exist before anything is multicast into its shared memory
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  const TileIter it = make_iter(d, P.total_tiles, MC);
   pdl_wait();                       // predecessor's results are visible from here on
 
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
-      for (int t = blockIdx.x; t < P.total_tiles; t += gridDim.x) {
-        TileCoord c = decode_tile(d, t);
+      for (int ti = it.first; ti < it.count; ti += it.step) {
+        TileCoord c = decode_tile(d, it.tile(ti));
         int kb = 0;  // running 64-wide K block index into the packed weights
         for (int s = 0; s < d.num_src; ++s) {
           for (int tap = 0; tap < d.taps; ++tap) {
@@ -370,7 +398,13 @@ __global__ void __launch_bounds__(kGemmThreads, 1) pf_gemm_kernel(const __grid_c
               mbar_expect_tx(&full_bar[stage], stage_bytes);
               if (d.a_mode == 0) tma_load_2d(sa, &P.tmA[s], &full_bar[stage], ch * kBlockK, c.m0);
               else tma_load_4d(sa, &P.tmA[s], &full_bar[stage], ch * kBlockK, c.x0 + dx, c.y0 + dy, c.img);
-              tma_load_2d(sb, &P.tmB, &full_bar[stage], kb * kBlockK, c.n0);
+              if (MC) {
+                const int half_rows = d.block_n >> 1;
+                tma_load_2d_mc(sb + it.rank * half_rows * 128, &P.tmBh, &full_bar[stage], kb * kBlockK,
+                               c.n0 + it.rank * half_rows, static_cast<uint16_t>(3));
+              } else {
+                tma_load_2d(sb, &P.tmB, &full_bar[stage], kb * kBlockK, c.n0);
+              }
               if (++stage == stages) { stage = 0; phase ^= 1; }
             }
           }
@@ -383,7 +417,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) pf_gemm_kernel(const __grid_c
       const uint32_t idesc = umma_idesc_bf16(kBlockM, d.block_n);
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
-      for (int t = blockIdx.x; t < P.total_tiles; t += gridDim.x) {
+      for (int ti = it.first; ti < it.count; ti += it.step) {
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + acc * d.block_n;
@@ -398,7 +432,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1) pf_gemm_kernel(const __grid_c
             // advance 16 bf16 = 32 B along K inside the 128-B swizzle row: +2 in the (addr>>4) field
             umma_bf16(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (ks | k) != 0);
           }
-          umma_commit(&empty_bar[stage]);            // frees this smem stage once the MMAs above retire
+          if (MC) umma_commit_mc(&empty_bar[stage], static_cast<uint16_t>(3));   // release the stage in both CTAs
+          else umma_commit(&empty_bar[stage]);       // frees this smem stage once the MMAs above retire
           if (++stage == stages) { stage = 0; phase ^= 1; }
         }
         umma_commit(&tmem_full[acc]);                // accumulator complete -> epilogue
@@ -407,11 +442,12 @@ __global__ void __launch_bounds__(kGemmThreads, 1) pf_gemm_kernel(const __grid_c
     }
   } else {
     // ===================== epilogue (warps 2..5) =====================
-    epilogue_loop(d, P.total_tiles, tmem_full, tmem_empty, tmem_base, warp, lane, tail_smem);
+    epilogue_loop(d, it, tmem_full, tmem_empty, tmem_base, warp, lane, tail_smem);
   }
 
   tc_fence_before();
   __syncthreads();
+  if (MC) cluster_sync_all();       // no CTA exits while its peer may still multicast into it / arrive on its barriers
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
@@ -580,7 +616,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) pf_conv3_halo_kernel(const __
       }
     }
   } else {
-    epilogue_loop(d, P.total_tiles, tmem_full, tmem_empty, tmem_base, warp, lane, tail_smem);
+    epilogue_loop(d, make_iter(d, P.total_tiles, false), tmem_full, tmem_empty, tmem_base, warp, lane, tail_smem);
   }
   tc_fence_before();
   __syncthreads();
@@ -595,12 +631,14 @@ __global__ void __launch_bounds__(kGemmThreads, 1) pf_conv3_halo_kernel(const __
 // ------------------------------------------------------------------------------------------------------------
 static int g_sm_counts[kMaxDevices] = {0};
 
-int gemm_launch(const GemmDesc& d, const CUtensorMap* tmA, const CUtensorMap& tmB, cudaStream_t stream) {
+int gemm_launch(const GemmDesc& d, const CUtensorMap* tmA, const CUtensorMap& tmB, const CUtensorMap* tmBh,
+                cudaStream_t stream) {
   static bool attr_done[kMaxDevices] = {false};
   const int kMaxSmem = 227 * 1024;
   const int dev = current_device();
   if (!attr_done[dev]) {
-    cudaError_t e = cudaFuncSetAttribute(pf_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
+    cudaError_t e = cudaFuncSetAttribute(pf_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(pf_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
     if (e != cudaSuccess) return set_error("cudaFuncSetAttribute(pf_gemm_kernel): %s", cudaGetErrorString(e));
     e = cudaFuncSetAttribute(pf_conv3_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
     if (e != cudaSuccess) return set_error("cudaFuncSetAttribute(pf_conv3_halo_kernel): %s", cudaGetErrorString(e));
@@ -622,6 +660,7 @@ int gemm_launch(const GemmDesc& d, const CUtensorMap* tmA, const CUtensorMap& tm
   for (int s = 0; s < d.num_src; ++s) P.tmA[s] = tmA[s];
   for (int s = d.num_src; s < 3; ++s) P.tmA[s] = tmA[0];
   P.tmB = tmB;
+  P.tmBh = tmBh ? *tmBh : tmB;
   P.d = d;
   P.kc = 1;
   int stage_bytes = kATileBytes + d.block_n * kBlockK * 2;
@@ -653,8 +692,23 @@ int gemm_launch(const GemmDesc& d, const CUtensorMap* tmA, const CUtensorMap& tm
     size_t hsmem = 1024 + static_cast<size_t>(kHaloSlots) * kHaloSlot + static_cast<size_t>(hstages) * b_bytes + kTailBytes;
     cudaError_t le = launch_pdl(pf_conv3_halo_kernel, dim3(grid), dim3(kGemmThreads), hsmem, stream, P);
     if (le != cudaSuccess) return set_error("pf_conv3_halo_kernel launch: %s", cudaGetErrorString(le));
+  } else if (tmBh != nullptr) {
+    // weight-multicast pairs: clusters of 2 CTAs over (m-tile pair, n-tile) work items
+    const int pairs = ((d.m_tiles + 1) / 2) * d.n_tiles;
+    const int clusters = pairs < g_sm_count / 2 ? pairs : g_sm_count / 2;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * clusters); cfg.blockDim = dim3(kGemmThreads); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+    cudaLaunchAttribute at[2];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = pdl_enabled() ? 2 : 1;
+    cudaError_t le = cudaLaunchKernelEx(&cfg, pf_gemm_kernel<true>, P);
+    if (le != cudaSuccess) return set_error("pf_gemm_kernel<multicast> launch: %s", cudaGetErrorString(le));
   } else {
-    cudaError_t le = launch_pdl(pf_gemm_kernel, dim3(grid), dim3(kGemmThreads), smem, stream, P);
+    cudaError_t le = launch_pdl(pf_gemm_kernel<false>, dim3(grid), dim3(kGemmThreads), smem, stream, P);
     if (le != cudaSuccess) return set_error("pf_gemm_kernel launch: %s", cudaGetErrorString(le));
   }
   cudaError_t e = cudaGetLastError();

@@ -67,7 +67,9 @@ void count_launch(const char* name);
 void note_work(double flops, const char* fmt, ...);
 int check_launch(const char* what);
 
-int gemm_launch(const GemmDesc& d, const CUtensorMap* tmA, const CUtensorMap& tmB, cudaStream_t stream);
+// tmBh != nullptr selects the weight-multicast variant (clusters of 2 CTAs): a {64, block_n / 2} box map of the weights
+int gemm_launch(const GemmDesc& d, const CUtensorMap* tmA, const CUtensorMap& tmB, const CUtensorMap* tmBh,
+                cudaStream_t stream);
 
 // Tensor maps (driver entry point fetched at run time; cached by key).
 int tmap_2d_bf16(CUtensorMap* out, const void* ptr, uint64_t cols, uint64_t rows, uint64_t ld_elems, uint32_t box_cols,

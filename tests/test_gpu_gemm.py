@@ -55,6 +55,42 @@ def test_linear_f32_and_layerscale(cuda):
     check('x += gamma*(xW+b)', xres, res + gamma * ref, 2e-5)
 
 
+@pytest.mark.parametrize('M,K,N,mode', [(9333, 1024, 1024, 'gamma'), (4148, 1024, 4096, 'gelu'), (9333, 1024, 3072, 'bf16'),
+                                        (20000, 32, 96, 'f32'), (9324, 592, 1024, 'f32'), (640, 256, 2048, 'bf16')])
+def test_linear_weight_multicast(cuda, M, K, N, mode):
+    """shapes that take the cluster-of-2 weight-multicast variant (>= 4 m-tiles, >= 148 tiles): odd m-tile counts
+    (73, 33: the last pair has an out-of-range m-tile), every epilogue flavour, block_n 256 / 96."""
+    ops = _ops()
+    g = torch.Generator(device='cuda').manual_seed(M + K + N)
+    x = torch.randn(M, K, device=cuda, generator=g)
+    w = torch.randn(N, K, device=cuda, generator=g) / K ** 0.5
+    b = torch.randn(N, device=cuda, generator=g)
+    pw = ops.pack_weight(w, b)
+    ld = ops.pad_to(K, 8)
+    xa = torch.zeros(M, ld, dtype=torch.bfloat16, device=cuda)
+    xa[:, :K] = bf(x)
+    ref = F.linear(rb(x), rb(w), b)
+    if mode == 'gamma':
+        res = torch.randn(M, N, device=cuda, generator=g)
+        gamma = torch.rand(N, device=cuda, generator=g)
+        out = res.clone()
+        d = ops.gemm(pw, [xa], out, gamma=gamma, src_c=[K])
+        check('mc x += gamma*(xW+b)', out, res + gamma * ref, 2e-5)
+    elif mode == 'gelu':
+        out = torch.zeros(M, N, dtype=torch.bfloat16, device=cuda)
+        d = ops.gemm(pw, [xa], out, act=ops.ACT_GELU, src_c=[K])
+        check('mc gelu', out, F.gelu(ref), 1e-2)
+    elif mode == 'f32':
+        out = torch.zeros(M, N, dtype=torch.float32, device=cuda)
+        d = ops.gemm(pw, [xa], out, src_c=[K])
+        check('mc fp32 out', out, ref, 2e-5)
+    else:
+        out = torch.zeros(M, N, dtype=torch.bfloat16, device=cuda)
+        d = ops.gemm(pw, [xa], out, src_c=[K])
+        check('mc bf16 out', out, ref, 1e-2)
+    assert d.m_tiles >= 4 and d.m_tiles * d.n_tiles >= 148
+
+
 def test_qkv_split_transposed_v(cuda):
     ops = _ops()
     g = torch.Generator(device='cuda').manual_seed(2)
