@@ -353,6 +353,13 @@ int pf_gemm(pf_gemm_desc* u, void* stream) {
   d.gamma = u->gamma;
   d.out = u->out; d.out_f32 = u->out_f32 || u->gamma != nullptr; d.out_ld = u->out_ld; d.out_col0 = u->out_col0;
   d.out2 = static_cast<__nv_bfloat16*>(u->out2); d.out2_ld = u->out2_ld;
+  if ((u->out_f32 || u->gamma) && reinterpret_cast<uintptr_t>(u->out) % 32 != 0)
+    return set_error("pf_gemm: fp32 outputs must be 32-byte aligned (256-bit epilogue stores)");
+  // 256-bit epilogue accesses need 32-byte aligned rows: bf16 pitches / offsets in multiples of 16 elements
+  d.wide = ((reinterpret_cast<uintptr_t>(u->out) | reinterpret_cast<uintptr_t>(u->out2) | reinterpret_cast<uintptr_t>(u->res1) |
+             reinterpret_cast<uintptr_t>(u->res2)) % 32 == 0) &&
+           u->out_col0 % 16 == 0 && (d.out_f32 || u->out_ld % 16 == 0) && (!u->out2 || u->out2_ld % 16 == 0) &&
+           (!(u->res1 || u->res2) || u->res_ld % 16 == 0);
   d.ps = u->ps > 1 ? u->ps : 1;
   d.n_logical = u->N;
   if (d.ps > 1) {

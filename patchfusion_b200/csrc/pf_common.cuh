@@ -254,6 +254,20 @@ __device__ __forceinline__ float gelu_erf(float x) {
   const float e = 1.0f - p * t * __expf(-u * u);
   return 0.5f * x * (1.0f + copysignf(e, x));
 }
+// ---------------------------------------------------------------- 256-bit global accesses (one full 32-B sector per thread)
+// A thread that owns an accumulator row writes 16-B pieces of 32 DIFFERENT rows per 128-bit store instruction: every
+// piece is half a sector, and partial-sector writes are what bounded the GEMM epilogues (read-modify-write in L2).
+__device__ __forceinline__ void ld_global_256(const void* p, uint32_t (&v)[8]) {
+  asm volatile("ld.global.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+               : "l"(p));
+}
+__device__ __forceinline__ void st_global_256(void* p, const uint32_t (&v)[8]) {
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(v[0]), "r"(v[1]), "r"(v[2]),
+               "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+               : "memory");
+}
+
 // ---------------------------------------------------------------- packed fp32x2 arithmetic (Blackwell FFMA2 / FADD2)
 __device__ __forceinline__ uint64_t pack2(uint32_t lo, uint32_t hi) {
   uint64_t r;

@@ -23,6 +23,7 @@ struct GemmDesc {
   const float* gamma;
   void* out;
   int out_f32, out_ld, out_col0;
+  int wide;              // every bf16 row pitch / column offset is a multiple of 16 elements: 256-bit accesses are aligned
   __nv_bfloat16* out2;
   int out2_ld;
   int ps, ps_cout_pad;   // pixel shuffle factor, per-tap column stride of the packed weight
