@@ -225,16 +225,27 @@ __global__ void __launch_bounds__(256) resize_bilinear_tiled_kernel(const bf16* 
         if (oy >= OH) break;
         const int y0 = s_y0[ty], y1 = s_y1[ty];
         const float fy = s_fy[ty];
-        float a[8], bb[8], c[8], d[8], o[8];
-        unpack8(patch[(y0 * kRsPW + x0) * 8 + ch], a);
-        unpack8(patch[(y0 * kRsPW + x1) * 8 + ch], bb);
-        unpack8(patch[(y1 * kRsPW + x0) * 8 + ch], c);
-        unpack8(patch[(y1 * kRsPW + x1) * 8 + ch], d);
+        // blend on packed FFMA2: a bf16 pair widens to an fp32 pair with a shift and a mask (this kernel was ALU-bound:
+        // ncu r01 sm__throughput 75 % at 41 % of DRAM peak)
+        const uint4 ua = patch[(y0 * kRsPW + x0) * 8 + ch], ub = patch[(y0 * kRsPW + x1) * 8 + ch];
+        const uint4 uc = patch[(y1 * kRsPW + x0) * 8 + ch], ud = patch[(y1 * kRsPW + x1) * 8 + ch];
         const float w00 = (1.f - fy) * (1.f - fx), w01 = (1.f - fy) * fx, w10 = fy * (1.f - fx), w11 = fy * fx;
+        const uint64_t p00 = pack2f(w00, w00), p01 = pack2f(w01, w01), p10 = pack2f(w10, w10), p11 = pack2f(w11, w11);
+        const uint32_t wa[4] = {ua.x, ua.y, ua.z, ua.w}, wb[4] = {ub.x, ub.y, ub.z, ub.w};
+        const uint32_t wc[4] = {uc.x, uc.y, uc.z, uc.w}, wd[4] = {ud.x, ud.y, ud.z, ud.w};
+        uint32_t ow[4];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) o[k] = w00 * a[k] + w01 * bb[k] + w10 * c[k] + w11 * d[k];
+        for (int k = 0; k < 4; ++k) {
+          uint64_t r = mul2(p00, pack2(wa[k] << 16, wa[k] & 0xffff0000u));
+          r = fma2(p01, pack2(wb[k] << 16, wb[k] & 0xffff0000u), r);
+          r = fma2(p10, pack2(wc[k] << 16, wc[k] & 0xffff0000u), r);
+          r = fma2(p11, pack2(wd[k] << 16, wd[k] & 0xffff0000u), r);
+          float lo, hi;
+          unpack2f(r, lo, hi);
+          ow[k] = pack_bf16(lo, hi);
+        }
         const size_t p = (static_cast<size_t>(b) * OH + oy) * OW + ox;
-        *reinterpret_cast<uint4*>(out + p * out_ld + out_col0 + slab * 64 + ch * 8) = pack8(o);
+        *reinterpret_cast<uint4*>(out + p * out_ld + out_col0 + slab * 64 + ch * 8) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
       }
     }
   }
@@ -452,14 +463,19 @@ __global__ void g2l_embed_kernel(const bf16* __restrict__ feat, int feat_ld, con
   x[idx] = __bfloat162float(feat[t * feat_ld + c]) + ape[idx];
 }
 
-// One CTA per (window, head); thread i < 144 owns query row i.  K/V of the window live in shared memory as fp32.
+// One CTA per (window, head); thread i < 144 owns query row i.  K / V of the window live in shared memory as fp32
+// PAIRS so both the q.k dot product and the p.v accumulation run on packed FFMA2 (all lanes read the same key: the
+// shared-memory reads are broadcasts).  Scores are kept in the log2 domain (scale * log2e folded into q, log2e into
+// the bias table and the -100 shift mask) and the online softmax rescales only when the running maximum moves - one
+// ex2 per key instead of two exps and an unconditional rescale (r01: 4.7 ms per image in this kernel).
 template <int HD>
 __global__ void __launch_bounds__(160) window_attention_kernel(const bf16* __restrict__ qkv,
                                                                const float* __restrict__ bias_table, int Hp, int Wp,
                                                                int C, int heads, int shift, bf16* __restrict__ out) {
-  constexpr int WS = 12, NT = 144;
-  __shared__ float sk[NT][HD + 1];
-  __shared__ float sv[NT][HD + 1];
+  constexpr int WS = 12, NT = 144, HP = HD / 2;
+  constexpr float kLog2e = 1.4426950408889634f;
+  __shared__ uint64_t sk[NT][HP];
+  __shared__ uint64_t sv[NT][HP];
   __shared__ float sb[529];
   __shared__ int stok[NT];
   __shared__ int sreg[NT];
@@ -468,7 +484,7 @@ __global__ void __launch_bounds__(160) window_attention_kernel(const bf16* __res
   const int wpr = Wp / WS;
   const int wy = win / wpr, wx = win - wy * wpr;
   const int tid = threadIdx.x;
-  for (int i = tid; i < 529; i += blockDim.x) sb[i] = bias_table[i * heads + head];
+  for (int i = tid; i < 529; i += blockDim.x) sb[i] = bias_table[i * heads + head] * kLog2e;
   if (tid < NT) {
     int iy = tid / WS, ix = tid - iy * WS;
     int ry = wy * WS + iy, rx = wx * WS + ix;                      // position in the rolled frame
@@ -479,43 +495,64 @@ __global__ void __launch_bounds__(160) window_attention_kernel(const bf16* __res
     sreg[tid] = shift > 0 ? hr * 3 + wr : 0;
   }
   __syncthreads();
-  for (int i = tid; i < NT * HD; i += blockDim.x) {
-    int t = i / HD, d = i - t * HD;
-    const bf16* row = qkv + static_cast<long long>(stok[t]) * (3 * C) + head * HD + d;
-    sk[t][d] = __bfloat162float(row[C]);
-    sv[t][d] = __bfloat162float(row[2 * C]);
+  for (int i = tid; i < NT * HP; i += blockDim.x) {
+    int t = i / HP, d = i - t * HP;
+    const bf16* row = qkv + static_cast<long long>(stok[t]) * (3 * C) + head * HD + 2 * d;
+    const float2 kk = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(row + C));
+    const float2 vv = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(row + 2 * C));
+    sk[t][d] = pack2f(kk.x, kk.y);
+    sv[t][d] = pack2f(vv.x, vv.y);
   }
   __syncthreads();
   if (tid >= NT) return;
-  const float scale = rsqrtf(static_cast<float>(HD));
-  float q[HD];
+  const float scale = rsqrtf(static_cast<float>(HD)) * kLog2e;
+  uint64_t q[HP], acc[HP];
   {
     const bf16* row = qkv + static_cast<long long>(stok[tid]) * (3 * C) + head * HD;
 #pragma unroll
-    for (int d = 0; d < HD; ++d) q[d] = __bfloat162float(row[d]) * scale;
+    for (int d = 0; d < HP; ++d) {
+      const float2 qq = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(row + 2 * d));
+      q[d] = pack2f(qq.x * scale, qq.y * scale);
+      acc[d] = 0;                                                  // (+0.0f, +0.0f)
+    }
   }
   const int iy = tid / WS, ix = tid - iy * WS, myreg = sreg[tid];
-  float m = -INFINITY, l = 0.f, acc[HD];
-#pragma unroll
-  for (int d = 0; d < HD; ++d) acc[d] = 0.f;
+  const float* brow = sb + (iy + WS - 1) * (2 * WS - 1) + (ix + WS - 1);
+  float m = -INFINITY, l = 0.f;
+  int jy = 0, jx = 0;
   for (int j = 0; j < NT; ++j) {
-    float s = 0.f;
+    uint64_t s2 = 0;
 #pragma unroll
-    for (int d = 0; d < HD; ++d) s += q[d] * sk[j][d];
-    int jy = j / WS, jx = j - jy * WS;
-    s += sb[(iy - jy + WS - 1) * (2 * WS - 1) + (ix - jx + WS - 1)];
-    if (sreg[j] != myreg) s += -100.0f;
-    float mn = fmaxf(m, s);
-    float a = __expf(m - mn), p = __expf(s - mn);
-    l = l * a + p;
+    for (int d = 0; d < HP; ++d) s2 = fma2(q[d], sk[j][d], s2);
+    float s0, s1;
+    unpack2f(s2, s0, s1);
+    float s = s0 + s1 + brow[-(jy * (2 * WS - 1) + jx)];
+    if (sreg[j] != myreg) s -= 100.0f * kLog2e;
+    if (++jx == WS) { jx = 0; ++jy; }
+    if (s > m) {                                                   // running maximum moves (rare after the first keys)
+      float a;
+      asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(a) : "f"(m - s));
+      const uint64_t a2 = pack2f(a, a);
 #pragma unroll
-    for (int d = 0; d < HD; ++d) acc[d] = acc[d] * a + p * sv[j][d];
-    m = mn;
+      for (int d = 0; d < HP; ++d) acc[d] = mul2(acc[d], a2);
+      l *= a;
+      m = s;
+    }
+    float p;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p) : "f"(s - m));
+    l += p;
+    const uint64_t p2 = pack2f(p, p);
+#pragma unroll
+    for (int d = 0; d < HP; ++d) acc[d] = fma2(p2, sv[j][d], acc[d]);
   }
   const float inv = 1.f / l;
   bf16* orow = out + static_cast<long long>(stok[tid]) * C + head * HD;
 #pragma unroll
-  for (int d = 0; d < HD; ++d) orow[d] = __float2bfloat16(acc[d] * inv);
+  for (int d = 0; d < HP; ++d) {
+    float a0, a1;
+    unpack2f(acc[d], a0, a1);
+    *reinterpret_cast<uint32_t*>(orow + 2 * d) = pack_bf16(a0 * inv, a1 * inv);
+  }
 }
 
 __global__ void swin_residual_crop_kernel(float* __restrict__ x, const float* __restrict__ y, int H, int W, int Wp, int C) {
