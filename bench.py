@@ -226,6 +226,20 @@ def lib_summary(records):
     return out
 
 
+def shard_plan_info(model, n_tiles, world):
+    """How the single image's tiles were distributed in the tile_sharded region (mirrors PatchFusion.forward)."""
+    from patchfusion_b200.parallel import tile_plan, shard_counts, block_rows
+    owner = world > 1 and model.shard_coarse == 'owner'
+    plan = tile_plan(n_tiles, world, model.owner_cost_tiles) if owner else None
+    rows = block_rows(n_tiles, world, plan)
+    coll = '1 all_gather_into_tensor of [%d, 392, 518] fp32 prediction blocks per image' % rows
+    if owner:
+        coll = '1 broadcast of rank 0\'s packed coarse depth + 6 coarse maps + 6 G2L maps, then ' + coll
+    return dict(coarse_stage='rank 0 computes + broadcasts, takes %.1f tiles less' % model.owner_cost_tiles if owner
+                else 'replicated on every rank', tiles_per_rank=shard_counts(n_tiles, world, plan),
+                collective=coll, tiles_on_busiest_rank=rows)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
@@ -426,6 +440,7 @@ def main():
             sys.stderr.write('%-26s %8.2f ms %6d launches %8.1f TF/s\n' % (k_, v['ms'], v['launches'],
                                                                          v['flops'] / max(v['ms'], 1e-9) / 1e9))
     cb = ge = None
+    plan_info = shard_plan_info(model, n_tiles, world)
     if not args.no_cpu_baseline and world == 1:
         del model
         torch.cuda.empty_cache()
@@ -436,8 +451,7 @@ def main():
     tile_sharded = dict(ms_per_image=ms_img_shard, tiles_per_s=n_tiles / (ms_img_shard / 1e3), n_gpus=world,
                         single_gpu_ms_per_image=ms_img_single, speedup_vs_single_gpu=ms_img_single / ms_img_shard,
                         efficiency_vs_n1=ms_img_single / ms_img_shard / world,
-                        collective='1 all_gather_into_tensor of [ceil(%d/%d), 392, 518] fp32 blocks per image' % (n_tiles, world),
-                        tiles_on_busiest_rank=-(-n_tiles // world))
+                        **plan_info)
     out = dict(
         metric='tiles/s', value=tps, unit='tiles/s', n_gpus=world, steps=args.steps, warmup=max(args.warmup, 3),
         ms_per_step=ms_dev / args.steps, higher_is_better=True, scaling='weak', vs_baseline=None, dtype='bf16',

@@ -118,6 +118,11 @@ class PatchFusion(ParamTree, PyTorchModelHubMixin):
         # coarse branch + G2L (batch 1) on a side stream next to the first fine branch: measured in DESIGN.md
         self.overlap_coarse = os.environ.get('PF_B200_OVERLAP_COARSE', '1') != '0'
         self._side_stream = None
+        # tile-sharded forward: 'owner' = rank 0 computes the per-image coarse branch + G2L, takes `owner_cost_tiles`
+        # fewer tiles and broadcasts the packed result; 'replicate' = every rank computes it (no broadcast)
+        self.shard_coarse = os.environ.get('PF_B200_SHARD_COARSE', 'owner')
+        self.owner_cost_tiles = float(os.environ.get('PF_B200_OWNER_COST', '2.7'))
+        self._pack = None
         self._mask_cache = {}
         # sub-module loads (model.fine_branch.load_state_dict(sd), as the load_branch constructor path does) and
         # .to()/.half() on a sub-module must drop the packed bf16 panels too: hook every container node
@@ -288,11 +293,46 @@ class PatchFusion(ParamTree, PyTorchModelHubMixin):
     def invalidate(self):
         """Drop the packed-weight engine and the captured graphs (call after editing parameters in place; state-dict
         loads and `.to()` on the model or any sub-module do it automatically)."""
-        self._engine, self._graphs = None, {}
+        self._engine, self._graphs, self._pack = None, {}, None
 
-    def _coarse_stage(self, eng, lr):
+    def _coarse_stage(self, eng, lr, pack=False):
+        """coarse branch + G2L of the whole image.  pack=True (tile-sharded owner): the results are copied into the
+        contiguous pack buffer that is broadcast, and every later stage reads the pack."""
         cd, cf = eng.branch('coarse', lr)
-        self._coarse = (cd[0], cf, eng.g2l(cf))
+        res = (cd[0], cf, eng.g2l(cf))
+        if not pack:
+            self._coarse = res
+            return
+        dst = self._pack[1]
+        dst[0].copy_(res[0])
+        for d, m in zip(dst[1] + dst[2], res[1] + res[2]):
+            d.t.copy_(m.t)
+        self._coarse = dst
+
+    def _ensure_pack(self, eng, lr):
+        """Pack buffer for the coarse results (coarse depth fp32, 6 coarse maps, 6 G2L maps; 256-B aligned segments).
+        Its layout follows from the model geometry alone; the first call runs the coarse stage once to read the
+        shapes off the stage outputs (every rank, outside any timed region)."""
+        if self._pack is not None and self._pack[2] is eng:
+            self._coarse = self._pack[1]
+            return self._pack[0]
+        from .engine import Map
+        cd, cf = eng.branch('coarse', lr)
+        g2l = eng.g2l(cf)
+        items = [(cd[0].shape, torch.float32, None)] + [(m.t.shape, m.t.dtype, m.C) for m in cf + g2l]
+        offs, total = [], 0
+        for shape, dt, _ in items:
+            offs.append(total)
+            total += (int(np.prod(shape)) * torch.empty((), dtype=dt).element_size() + 255) // 256 * 256
+        buf = eng.buf('coarse.pack', (total,), torch.uint8)
+        views = []
+        for (shape, dt, C), o in zip(items, offs):
+            nb = int(np.prod(shape)) * torch.empty((), dtype=dt).element_size()
+            t = buf[o:o + nb].view(dt).view(tuple(shape))
+            views.append(t if C is None else Map(t, C))
+        self._pack = (buf, (views[0], views[1:1 + len(cf)], views[1 + len(cf):]), eng)
+        self._coarse = self._pack[1]
+        return buf
 
     def _fine_stage(self, eng, img, T, geom, raw):
         """crop+resize -> fine branch for the T tiles whose raw origins are the device rows `raw` ([T,2] int32)."""
@@ -312,11 +352,20 @@ class PatchFusion(ParamTree, PyTorchModelHubMixin):
         crops, fd, ff, ws = fine
         eng.fusion(crops, boxes, fd, ff, cd, cf, g2l, depth_out=out, ws=ws)
 
-    def _image_stage(self, eng, lr, img, geom, sizes, io_raw, io_box, blk, with_coarse):
+    def _image_stage(self, eng, lr, img, geom, sizes, io_raw, io_box, blk, with_coarse, part='all'):
         """The static kernel sequence of one phase of one image on this rank: [coarse branch + G2L] and the
         micro-batches (fine branch + fusion each).  The coarse stage has no dependency on the first fine branch, so it
-        runs on a side stream next to it (its batch-1 kernels fill a fraction of the SMs)."""
+        runs on a side stream next to it (its batch-1 kernels fill a fraction of the SMs).
+        part='pre' / 'post' (tile-sharded, non-owner ranks): the fine branch of the first micro-batch runs BEFORE the
+        broadcast of the owner's coarse results arrives, everything else after it."""
         from . import lib
+        if part == 'pre':
+            self._pending_fine = self._fine_stage(eng, img, sizes[0], geom, io_raw[:sizes[0]])
+            return
+        if part == 'post':
+            T0 = sizes[0]
+            self._fusion_stage(eng, self._pending_fine, io_box[:T0], blk[:T0])
+            io_raw, io_box, blk, sizes = io_raw[T0:], io_box[T0:], blk[T0:], sizes[1:]
         cur = torch.cuda.current_stream()
         side = None
         if with_coarse:
@@ -344,16 +393,27 @@ class PatchFusion(ParamTree, PyTorchModelHubMixin):
             return [n // nchunk + (1 if i < n % nchunk else 0) for i in range(nchunk)]
         return [min(process_num, n - i * process_num) for i in range(nchunk)]     # the reference's split (BP:293)
 
-    def _compute_phase(self, eng, phase, lr, img, geom, raw, process_num, shard):
+    def _compute_phase(self, eng, phase, lr, img, geom, raw, process_num, shard, plan=None, group=None):
         """Fused predictions of this rank's tiles of the (global, ordered) tile list `raw` -> its block
-        [ceil(n / world), ph, pw] fp32 (row j = global tile rank + j * world)."""
-        from .parallel import shard_indices
+        [block_rows, ph, pw] fp32 (row j = the j-th tile of the list that `plan` gives to this rank)."""
+        from .parallel import shard_indices, block_rows
         H, W, h, w, ph, pw = geom
         rank, world = (0, 1) if shard is None else shard
         n = len(raw)
-        own = shard_indices(n, rank, world)
-        blk = eng.buf('pred.blk.' + phase, (max(-(-n // world), 1), ph, pw), torch.float32)
+        own = shard_indices(n, rank, world, plan)
+        blk = eng.buf('pred.blk.' + phase, (block_rows(n, world, plan), ph, pw), torch.float32)
+        with_coarse = phase == 'reg'
+        owner_mode = with_coarse and shard is not None and self.shard_coarse == 'owner'
+        real = shard is not None and self._real_shard
+        if owner_mode:
+            # rank 0 computes coarse + G2L into the pack and broadcasts it; the others start on their fine branch
+            pack = self._ensure_pack(eng, lr)
+            if rank == 0:
+                self._graphed(('coarse.pack',) + tuple(geom), lambda: self._coarse_stage(eng, lr, pack=True))
+            with_coarse = False
         if not own:
+            if owner_mode and real:
+                self._broadcast_pack(pack, group)
             return blk
         io_raw = eng.buf('io.raw.' + phase, (len(own), 2), torch.int32)
         io_box = eng.buf('io.box.' + phase, (len(own), 4), torch.float32)
@@ -365,15 +425,28 @@ class PatchFusion(ParamTree, PyTorchModelHubMixin):
             [[np.float32(x) * fx, np.float32(y) * fy, np.float32(x + w) * fx, np.float32(y + h) * fy]
              for (y, x) in chunk], dtype=np.float32)))
         sizes = self._micro_sizes(len(own), process_num)
-        with_coarse = phase == 'reg'
-        key = ('image', phase, tuple(sizes), blk.shape[0]) + tuple(geom)
-        self._graphed(key, lambda: self._image_stage(eng, lr, img, geom, sizes, io_raw, io_box, blk, with_coarse))
+        key = ('image', phase, tuple(sizes), blk.shape[0], with_coarse) + tuple(geom)
+        run = lambda part: self._graphed(key + (part,), lambda: self._image_stage(
+            eng, lr, img, geom, sizes, io_raw, io_box, blk, with_coarse, part))
+        if owner_mode and real:
+            if rank != 0:
+                run('pre')
+            self._broadcast_pack(pack, group)
+            run('post' if rank != 0 else 'all')
+        else:
+            run('all')
         return blk
+
+    @staticmethod
+    def _broadcast_pack(pack, group):
+        import torch.distributed as dist
+        dist.broadcast(pack, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
 
     def _exchange(self, compute, shard, group):
         """The ONE collective of the tile-sharded path: all-gather of the per-rank prediction blocks.
         shard=None: single device.  shard=('emulate', W): the W ranks are computed one after the other in this
         process (test hook for 1-GPU boxes; same blocks, same stitch)."""
+        self._real_shard = shard is not None and shard[0] != 'emulate'
         if shard is None:
             return compute(None)
         if shard[0] == 'emulate':
@@ -381,13 +454,13 @@ class PatchFusion(ParamTree, PyTorchModelHubMixin):
         from .parallel import gather_blocks
         return gather_blocks(compute(shard), shard[1], group)
 
-    def _stitch_phase(self, eng, phase, full, origins, world, th, tw, mask, up, base, canvas, want):
+    def _stitch_phase(self, eng, phase, full, origins, world, th, tw, mask, up, base, canvas, want, plan=None):
         """pf_stitch_gather over the global tile list (deterministic order) -> requested canvases."""
         from . import ops
         from .parallel import slot_table
         CH, CW = canvas
         n = len(origins)
-        slots = slot_table(n, world)
+        slots = slot_table(n, world, plan)
         tab = eng.buf('stitch.tab.' + phase, (n, 3), torch.int32)
         tab.copy_(torch.tensor([(oy, ox, sl) for (oy, ox), sl in zip(origins, slots)], dtype=torch.int32))
         dev = full.device
@@ -458,9 +531,14 @@ class PatchFusion(ParamTree, PyTorchModelHubMixin):
             raw += [(h * a + oy, w * b + ox) for a in range(ny) for b in range(nx)]
             proc += [(ph * a + py, pw * b + px) for a in range(ny) for b in range(nx)]
         is_r = cai_mode[0] == 'r'
-        full = self._exchange(lambda sh: self._compute_phase(eng, 'reg', lr, img, geom, raw, process_num, sh), shard, group)
+        plan = None
+        if shard is not None and self.shard_coarse == 'owner':
+            from .parallel import tile_plan
+            plan = tile_plan(len(raw), world, self.owner_cost_tiles)
+        full = self._exchange(lambda sh: self._compute_phase(eng, 'reg', lr, img, geom, raw, process_num, sh, plan, group),
+                              shard, group)
         outs = self._stitch_phase(eng, 'reg', full, proc, world, ph, pw, mask, (0, 0), None, (RH, RW),
-                                  ('num', 'den') if is_r else ('avg',))
+                                  ('num', 'den') if is_r else ('avg',), plan)
         if is_r:
             from . import ops
             n2 = torch.empty((H, W), dtype=torch.float32, device=dev)

@@ -59,7 +59,9 @@ def test_vitl_4k_p16_full_canvas(cuda, vitl):
 def test_vitl_4k_p49_full_canvas_and_invariances(cuda, vitl):
     """configs[2]: Depth-Anything-vitl, 4K, P49 (m2: 16+12+12+9 tiles in 9,9,9,9,9,4 micro-batches) - the canvas
     bench.py times - against the oracle; then the canvas is BIT-identical for another micro-batch size and for the
-    tile-sharded decomposition over 8 ranks (7,6,..,6 tiles; emulated rank by rank on this one GPU)."""
+    tile-sharded decomposition over 8 ranks, emulated rank by rank on this one GPU: the coarse-owner plan (rank 0
+    computes coarse + G2L into the broadcast pack and takes 4 tiles, the others 7,7,7,6,6,6,6) and the replicated
+    round-robin plan (7,6,..,6)."""
     v = vitl
     with torch.no_grad():
         want = v['orc'].infer(v['lr'], v['img'], cai_mode='m2', process_num=4)
@@ -70,11 +72,14 @@ def test_vitl_4k_p49_full_canvas_and_invariances(cuda, vitl):
     d = (g4 - got).abs().max().item()
     print('process_num 9 vs 4: max diff %.3e' % d)
     assert d == 0.0, 'tiles are independent and the stitch order is fixed: grouping must not change a bit'
-    g8, _ = v['model'](mode='infer', image_lr=v['lr'], image_hr=v['img'], cai_mode='m2', process_num=9,
-                       shard=('emulate', 8))
-    d = (g8 - got).abs().max().item()
-    print('8-way tile sharding vs single: max diff %.3e' % d)
-    assert d == 0.0
+    for how in ('owner', 'replicate'):
+        v['model'].shard_coarse = how
+        g8, _ = v['model'](mode='infer', image_lr=v['lr'], image_hr=v['img'], cai_mode='m2', process_num=9,
+                           shard=('emulate', 8))
+        d = (g8 - got).abs().max().item()
+        print('8-way tile sharding (%s) vs single: max diff %.3e' % (how, d))
+        assert d == 0.0
+    v['model'].shard_coarse = 'owner'
 
 
 def test_vitb_8k_8x8_r128(cuda):

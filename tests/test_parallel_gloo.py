@@ -7,7 +7,8 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from patchfusion_b200.parallel import gather_blocks, shard_counts, shard_indices, slot_table, stitch_reference
+from patchfusion_b200.parallel import (block_rows, gather_blocks, shard_counts, shard_indices, slot_table,
+                                       stitch_reference, tile_plan)
 
 pytestmark = pytest.mark.timeout(300)
 
@@ -28,6 +29,27 @@ def test_shard_plan():
     assert shard_counts(49, 8) == [7, 6, 6, 6, 6, 6, 6, 6]
 
 
+def test_owner_plan():
+    """tile_plan: owner_cost = 0 is round-robin; with a cost the owner gets that many fewer items, every item has one
+    owner and the slot table is a bijection into the rank-major gathered blocks."""
+    for n, w in [(49, 8), (10, 4), (3, 4), (0, 2)]:
+        assert tile_plan(n, w) == [i % w for i in range(n)]
+        assert slot_table(n, w, tile_plan(n, w)) == slot_table(n, w)
+    plan = tile_plan(49, 8, owner_cost=2.7)
+    assert shard_counts(49, 8, plan) == [4, 7, 7, 7, 6, 6, 6, 6]
+    assert shard_counts(49, 2, tile_plan(49, 2, 2.7)) == [23, 26]
+    for n, w, c in [(49, 8, 2.7), (49, 2, 2.7), (353, 8, 2.7), (5, 8, 2.7), (16, 4, 100.0)]:
+        plan = tile_plan(n, w, c)
+        per = block_rows(n, w, plan)
+        owned = [shard_indices(n, r, w, plan) for r in range(w)]
+        assert sorted(i for o in owned for i in o) == list(range(n))
+        slots = slot_table(n, w, plan)
+        assert len(set(slots)) == n
+        for r in range(w):
+            assert [slots[i] for i in owned[r]] == [r * per + j for j in range(len(owned[r]))]
+    assert shard_counts(16, 4, tile_plan(16, 4, 100.0))[0] == 0      # an owner that is too busy gets no tiles
+
+
 def _worker(rank, world, port, out):
     os.environ['MASTER_ADDR'] = '127.0.0.1'
     os.environ['MASTER_PORT'] = str(port)
@@ -38,16 +60,18 @@ def _worker(rank, world, port, out):
     n = len(origins)
     tiles = torch.rand(n, th, tw, generator=g)
     mask = torch.rand(th, tw, generator=g) + 1e-3
-    own = shard_indices(n, rank, world)
-    per = -(-n // world)
-    block = torch.full((per, th, tw), float('nan'))           # padding rows must never be read
-    for j, i in enumerate(own):
-        block[j] = tiles[i]
-    full = gather_blocks(block, world)
-    assert full.shape == (world * per, th, tw)
-    num, den = stitch_reference(full, origins, slot_table(n, world), mask, shape)
     full_n, full_d = stitch_reference(tiles, origins, list(range(n)), mask, shape)
-    same = torch.equal(num, full_n) and torch.equal(den, full_d)
+    same = True
+    for plan in (None, tile_plan(n, world, owner_cost=2.7)):  # round-robin and the coarse-owner plan
+        own = shard_indices(n, rank, world, plan)
+        per = block_rows(n, world, plan)
+        block = torch.full((per, th, tw), float('nan'))       # padding rows must never be read
+        for j, i in enumerate(own):
+            block[j] = tiles[i]
+        full = gather_blocks(block, world)
+        assert full.shape == (world * per, th, tw)
+        num, den = stitch_reference(full, origins, slot_table(n, world, plan), mask, shape)
+        same = same and torch.equal(num, full_n) and torch.equal(den, full_d)
     if rank == 0:
         out.put(same)
     dist.barrier()

@@ -18,18 +18,22 @@ model = model.to(dev).eval()
 img = torch.rand(1, 3, 1080, 1920, generator=torch.Generator().manual_seed(0)).to(dev)
 lr = model.make_lr(img)
 ok = True
-for mode in ('m1', 'm2', 'r4'):
-    random.seed(0)
-    ref, _ = model(mode='infer', image_lr=lr, image_hr=img, cai_mode=mode, process_num=2)
-    ref = ref.clone()
-    random.seed(0)
-    y, _ = model(mode='infer', image_lr=lr, image_hr=img, cai_mode=mode, process_num=2, shard=(rank, world))
-    err = (y - ref).abs().max().item()
-    t = torch.tensor([err], device=dev)
-    dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    if rank == 0:
-        print('%s: world %d  max|sharded - single| = %.3e (range %.3f..%.3f)' % (mode, world, t.item(), ref.min().item(), ref.max().item()), flush=True)
-    ok = ok and t.item() == 0.0          # deterministic stitch over gathered prediction blocks: bit-identical
+for how in ('owner', 'replicate'):       # coarse stage on rank 0 + broadcast / replicated on every rank
+    model.shard_coarse = how
+    for mode in ('m1', 'm2', 'r4'):
+        random.seed(0)
+        ref, _ = model(mode='infer', image_lr=lr, image_hr=img, cai_mode=mode, process_num=2)
+        ref = ref.clone()
+        for rep in range(2):             # second pass replays the captured graphs
+            random.seed(0)
+            y, _ = model(mode='infer', image_lr=lr, image_hr=img, cai_mode=mode, process_num=2, shard=(rank, world))
+            err = (y - ref).abs().max().item()
+            t = torch.tensor([err], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            if rank == 0:
+                print('%s %s pass %d: world %d  max|sharded - single| = %.3e (range %.3f..%.3f)'
+                      % (how, mode, rep, world, t.item(), ref.min().item(), ref.max().item()), flush=True)
+            ok = ok and t.item() == 0.0  # deterministic stitch over gathered prediction blocks: bit-identical
 dist.barrier()
 dist.destroy_process_group()
 sys.exit(0 if ok else 1)
