@@ -99,11 +99,11 @@ static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> g_maps;
 static std::mutex g_maps_mu;
 
 static int encode(CUtensorMap* out, const void* ptr, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-                  const uint32_t* box) {
+                  const uint32_t* box, CUtensorMapDataType dt = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16) {
   MapKey key;
   memset(&key, 0, sizeof(key));
   key.v[0] = reinterpret_cast<uint64_t>(ptr);
-  key.v[1] = static_cast<uint64_t>(rank);
+  key.v[1] = static_cast<uint64_t>(rank) | (static_cast<uint64_t>(dt) << 8);
   for (int i = 0; i < rank; ++i) {
     key.v[2 + i] = dims[i];
     key.v[6 + i] = (i + 1 < rank ? strides_bytes[i] : 0) ^ (static_cast<uint64_t>(box[i]) << 48);
@@ -124,7 +124,7 @@ static int encode(CUtensorMap* out, const void* ptr, int rank, const uint64_t* d
     gstr[i] = strides_bytes[i];
     if (gstr[i] & 15) return set_error("tensor map: stride %d (%llu B) not a multiple of 16", i, (unsigned long long)gstr[i]);
   }
-  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(ptr), gdim, gstr, bx, es,
+  CUresult r = fn(out, dt, rank, const_cast<void*>(ptr), gdim, gstr, bx, es,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
@@ -145,6 +145,13 @@ int tmap_2d_bf16(CUtensorMap* out, const void* ptr, uint64_t cols, uint64_t rows
   uint64_t str[1] = {ld * 2};
   uint32_t box[2] = {box_cols, box_rows};
   return encode(out, ptr, 2, dims, str, box);
+}
+int tmap_2d_f32(CUtensorMap* out, const void* ptr, uint64_t cols, uint64_t rows, uint64_t ld, uint32_t box_cols,
+                uint32_t box_rows) {
+  uint64_t dims[2] = {cols, rows};
+  uint64_t str[1] = {ld * 4};
+  uint32_t box[2] = {box_cols, box_rows};
+  return encode(out, ptr, 2, dims, str, box, CU_TENSOR_MAP_DATA_TYPE_FLOAT32);
 }
 int tmap_3d_bf16(CUtensorMap* out, const void* ptr, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t ld1, uint64_t ld2,
                  uint32_t b0, uint32_t b1, uint32_t b2) {
@@ -387,7 +394,27 @@ int pf_gemm(pf_gemm_desc* u, void* stream) {
                   static_cast<long long>(d.m_tiles) * d.n_tiles >= 148;
   CUtensorMap tmBh;
   if (mc && tmap_2d_bf16(&tmBh, u->w_ptr, u->Ktot, n_pad, u->Ktot, 64, bn / 2)) return 1;
-  return gemm_launch(d, tmA, tmB, mc ? &tmBh : nullptr, static_cast<cudaStream_t>(stream));
+  // Epilogue through shared memory + TMA (pf_gemm_kernel only): plain bf16 outputs in 64-column groups, fp32 outputs
+  // and the fp32 residual stream (x += gamma * v) in 32-column chunks.  PF_B200_NO_TMA_EPI=1 keeps the direct stores.
+  static const bool no_tma_epi = getenv("PF_B200_NO_TMA_EPI") != nullptr;
+  CUtensorMap tmOut;
+  d.tma_out = 0;
+  if (!no_tma_epi && !halo && d.ps == 1 && !d.w2 && !d.res1 && !d.res2 && !d.out2) {
+    const uint64_t ocols = static_cast<uint64_t>(u->out_col0) + u->N;     // columns >= N are clipped by the copy
+    if (!d.out_f32 && bn % 64 == 0 && reinterpret_cast<uintptr_t>(u->out) % 16 == 0) {
+      if (u->a_mode == 0) {
+        if (tmap_2d_bf16(&tmOut, u->out, ocols, u->M, u->out_ld, 64, 32)) return 1;
+      } else {
+        const uint32_t bwx = d.bw < 32 ? d.bw : 32;
+        if (tmap_4d_nhwc_bf16(&tmOut, u->out, ocols, u->W, u->H, u->NB, u->out_ld, 64, bwx, 32 / bwx)) return 1;
+      }
+      d.tma_out = 1;
+    } else if (d.out_f32 && u->a_mode == 0 && u->out_ld % 4 == 0 && reinterpret_cast<uintptr_t>(u->out) % 16 == 0) {
+      if (tmap_2d_f32(&tmOut, u->out, ocols, u->M, u->out_ld, 32, 32)) return 1;
+      d.tma_out = 2;
+    }
+  }
+  return gemm_launch(d, tmA, tmB, mc ? &tmBh : nullptr, d.tma_out ? &tmOut : nullptr, static_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"

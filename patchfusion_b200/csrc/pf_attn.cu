@@ -170,7 +170,10 @@ __global__ void __launch_bounds__(kAttnThreads, 1) pf_attention_kernel(const __g
 
   if (warp == kSoftmaxWarps) {
     // ===================== TMA producer =====================
-    if (lane == 0) {
+    // The issuing warps walk their loops as WHOLE warps (uniform control flow keeps barrier addresses, descriptors and
+    // counters in uniform registers) and one elected lane issues: inside `if (lane == 0)` every tcgen05.mma / TMA
+    // paid an ELECT / R2UR.BROADCAST round trip (~13 instructions) on the serial S -> P -> PV critical path.
+    {
       int ks = 0, vs = 0;
       uint32_t kph = 0, vph = 0, qe_ph = 0;
       for (int item = blockIdx.x; item < P.n_items; item += gridDim.x) {
@@ -178,18 +181,24 @@ __global__ void __launch_bounds__(kAttnThreads, 1) pf_attention_kernel(const __g
         const int h = bh % P.heads, b = bh / P.heads;
         const int q0 = pair * 2 * kQTile;
         mbar_wait(q_empty, qe_ph ^ 1); qe_ph ^= 1;
-        mbar_expect_tx(q_full, 2 * kTileBytes);
-        tma_load_3d(sQ, &P.tmQK, q_full, h * kHd, q0, b);
-        tma_load_3d(sQ + kTileBytes, &P.tmQK, q_full, h * kHd, q0 + kQTile, b);   // rows >= seq are zero-filled
+        if (elect_one()) {
+          mbar_expect_tx(q_full, 2 * kTileBytes);
+          tma_load_3d(sQ, &P.tmQK, q_full, h * kHd, q0, b);
+          tma_load_3d(sQ + kTileBytes, &P.tmQK, q_full, h * kHd, q0 + kQTile, b);   // rows >= seq are zero-filled
+        }
         for (int j = 0; j < nkv; ++j) {
           mbar_wait(&k_empty[ks], kph ^ 1);
-          mbar_expect_tx(&k_full[ks], kTileBytes);
-          tma_load_3d(sK + ks * kTileBytes, &P.tmQK, &k_full[ks], P.D + h * kHd, j * kKTile, b);
+          if (elect_one()) {
+            mbar_expect_tx(&k_full[ks], kTileBytes);
+            tma_load_3d(sK + ks * kTileBytes, &P.tmQK, &k_full[ks], P.D + h * kHd, j * kKTile, b);
+          }
           if (++ks == kKS) { ks = 0; kph ^= 1; }
           mbar_wait(&v_empty[vs], vph ^ 1);
-          mbar_expect_tx(&v_full[vs], kTileBytes);
-          tma_load_2d(sV + vs * kTileBytes, &P.tmVt, &v_full[vs], j * kKTile, (b * P.heads + h) * kHd);
-          tma_load_2d(sV + vs * kTileBytes + 8192, &P.tmVt, &v_full[vs], j * kKTile + 64, (b * P.heads + h) * kHd);
+          if (elect_one()) {
+            mbar_expect_tx(&v_full[vs], kTileBytes);
+            tma_load_2d(sV + vs * kTileBytes, &P.tmVt, &v_full[vs], j * kKTile, (b * P.heads + h) * kHd);
+            tma_load_2d(sV + vs * kTileBytes + 8192, &P.tmVt, &v_full[vs], j * kKTile + 64, (b * P.heads + h) * kHd);
+          }
           if (++vs == kVS) { vs = 0; vph ^= 1; }
         }
       }
@@ -197,7 +206,7 @@ __global__ void __launch_bounds__(kAttnThreads, 1) pf_attention_kernel(const __g
   } else if (warp == kSoftmaxWarps + 1) {
     // ===================== QK^T issuer: S_t = Q_t K_j^T as soon as the softmax warps have taken S_t =====================
     // (a separate thread from the PV issuer, so a QK^T is never queued behind a wait for P)
-    if (lane == 0) {
+    {
       int ks = 0;
       uint32_t kph = 0, qf_ph = 0;
       uint32_t sfree_ph[2] = {0, 0};
@@ -218,22 +227,24 @@ __global__ void __launch_bounds__(kAttnThreads, 1) pf_attention_kernel(const __g
             if (t < nt) {
               mbar_wait(&s_free[t], sfree_ph[t] ^ 1); sfree_ph[t] ^= 1;
               tc_fence_after();
-              ATTN_TRACE(1, t, j, 0);
+              if (lane == 0) ATTN_TRACE(1, t, j, 0);
               const uint64_t dq = dq0 + t * (kTileBytes >> 4);
+              if (elect_one()) {
 #pragma unroll
-              for (int k = 0; k < 4; ++k) umma_bf16(tmem_base + kColS + t * 128, dq + 2 * k, dk + 2 * k, idesc_s, k != 0);
-              umma_commit(&s_full[t]);
+                for (int k = 0; k < 4; ++k) umma_bf16(tmem_base + kColS + t * 128, dq + 2 * k, dk + 2 * k, idesc_s, k != 0);
+                umma_commit(&s_full[t]);
+              }
             }
           }
-          umma_commit(&k_empty[ks]);
+          if (elect_one()) umma_commit(&k_empty[ks]);
           if (++ks == kKS) { ks = 0; kph ^= 1; }
         }
-        umma_commit(q_empty);                                  // every QK^T of the item is issued: Q may be replaced
+        if (elect_one()) umma_commit(q_empty);                 // every QK^T of the item is issued: Q may be replaced
       }
     }
   } else if (warp == kSoftmaxWarps + 2) {
     // ===================== PV issuer: O_t += P_t V_j (A operand = P in TMEM) =====================
-    if (lane == 0) {
+    {
       const uint32_t idesc_o = umma_idesc_bf16(128, kHd);
       int vs = 0;
       uint32_t vph = 0;
@@ -253,14 +264,22 @@ __global__ void __launch_bounds__(kAttnThreads, 1) pf_attention_kernel(const __g
               mbar_wait(&p_full[t], pfull_ph[t]); pfull_ph[t] ^= 1;
               if (j == 0) { mbar_wait(&o_free[t], ofree_ph[t] ^ 1); ofree_ph[t] ^= 1; }
               tc_fence_after();
-              ATTN_TRACE(2, t, j, 0);
+              if (lane == 0) ATTN_TRACE(2, t, j, 0);
               const uint32_t tO = tmem_base + kColO + t * 64, tP = tmem_base + kColP + t * 64;
-              for (int k = 0; k < nk; ++k)
-                umma_bf16_ts(tO, tP + k * 8, (k < 4 ? dv0 : dv1) + 2 * (k & 3), idesc_o, (j | k) != 0);
-              umma_commit(&o_done[t]);
+              if (elect_one()) {
+                if (nk == 8) {
+#pragma unroll
+                  for (int k = 0; k < 8; ++k)
+                    umma_bf16_ts(tO, tP + k * 8, (k < 4 ? dv0 : dv1) + 2 * (k & 3), idesc_o, (j | k) != 0);
+                } else {
+                  for (int k = 0; k < nk; ++k)
+                    umma_bf16_ts(tO, tP + k * 8, (k < 4 ? dv0 : dv1) + 2 * (k & 3), idesc_o, (j | k) != 0);
+                }
+                umma_commit(&o_done[t]);
+              }
             }
           }
-          umma_commit(&v_empty[vs]);
+          if (elect_one()) umma_commit(&v_empty[vs]);
           if (++vs == kVS) { vs = 0; vph ^= 1; }
         }
       }

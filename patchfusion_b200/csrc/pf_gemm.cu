@@ -38,6 +38,7 @@ struct GemmKernelParams {
   CUtensorMap tmA[3];
   CUtensorMap tmB;
   CUtensorMap tmBh;     // multicast variant: box of block_n / 2 weight rows (each CTA of the pair fetches one half)
+  CUtensorMap tmOut;    // d.tma_out: output tensor (bf16 {64 cols, 32 rows} boxes, or fp32 {32 cols, 32 rows})
   GemmDesc d;
   int stages;
   int total_tiles;
@@ -69,11 +70,45 @@ __device__ __forceinline__ TileCoord decode_tile(const GemmDesc& d, int t) {
 }
 
 
+// Columns the MMA of tile t must produce: block_n, or for the last n-tile the remaining columns rounded up to 16.
+__device__ __forceinline__ int tile_n_eff(const GemmDesc& d, int t) {
+  const int n0 = (t % d.n_tiles) * d.block_n;
+  const int rem = ((d.N - n0 + 15) >> 4) << 4;
+  return rem < d.block_n ? rem : d.block_n;
+}
+// K = 16 steps that carry data in the last 64-channel chunk of source s (the rest of the chunk is TMA zero fill).
+__device__ __forceinline__ int last_chunk_k16(const GemmDesc& d, int s) {
+  return (d.k_true[s] - (d.chunks[s] - 1) * kBlockK + 15) >> 4;
+}
+
+// Debug timeline (build with -DPF_GEMM_TRACE, tools/gemm_trace.py): CTA 0 records (role, tile, event, clock).  Every
+// recording thread owns a 256-entry region and a private counter: a trace point is one clock read and two stores.
+#ifdef PF_GEMM_TRACE
+__device__ unsigned long long g_gemm_trace[4 * 256 * 2];
+__device__ __forceinline__ void gemm_trace(int role, int t, int ev, unsigned int& cnt) {
+  if (blockIdx.x != 0 || cnt >= 256) return;
+  const unsigned int i = role * 256 + cnt++;
+  g_gemm_trace[2 * i] = (1ull << 63) | (static_cast<unsigned long long>(role) << 48) |
+                        (static_cast<unsigned long long>(t) << 16) | static_cast<unsigned long long>(ev);
+  g_gemm_trace[2 * i + 1] = clock64();
+}
+#define GEMM_TRACE(role, t, ev) gemm_trace(role, t, ev, trace_cnt)
+#define GEMM_TRACE_DECL unsigned int trace_cnt = 0;
+#else
+#define GEMM_TRACE(role, t, ev)
+#define GEMM_TRACE_DECL
+#endif
+
 // One 32-column chunk of one accumulator row: bias -> activation -> residuals -> store.  FULL == all 32 columns exist
 // (vector loads/stores, no predication); the tail variant predicates every column but keeps all indices static so
 // f[] stays in registers.
 constexpr int kMaxTail = 16;   // widest fused trailing 1x1 layer
 constexpr int kTailBytes = 512 + 128 * kMaxTail * 4;   // barriers + TMEM slot + [128][kMaxTail] fp32 scratch
+// pf_gemm_kernel: one 4 KB staging tile (32 rows x 128 B, SWIZZLE_128B) per epilogue warp for the TMA-store epilogue; the
+// fused-tail scratch (never used together with it) aliases the same bytes
+constexpr int kStageTile = 32 * 128;
+constexpr int kEpiStageBytes = kEpiWarps * kStageTile;  // 32 KB
+constexpr int kEpiSmemBytes = 512 + kEpiStageBytes;
 
 // W = chunk width in accumulator columns (32, or 16 when the two warps of a quadrant split an unpaired chunk);
 // TAILN = compile-time bound on the fused trailing layer's outputs (0 = no trailing layer): keeps the executed code
@@ -299,6 +334,140 @@ __device__ __forceinline__ void epilogue_row(const GemmDesc& d, uint32_t taddr, 
   if (nchunks & 1) epilogue_cols<16, TAILN>(d, taddr, paired * 32 + half * 16, c, ocol0, orow, row_ok, y2);
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// Epilogue through shared memory + TMA (pf_gemm_kernel, d.tma_out != 0).
+// A thread owns one accumulator row, so direct global accesses are 32-byte pieces of 32 different rows per instruction:
+// one L2 request per sector.  The in-kernel timeline (tools/gemm_trace.py) showed what that costs: a 128 x 256 tile
+// of the ViT linears is 4096 128-byte operand requests, its epilogue another 2048 (bf16) to 8192 (fp32 residual stream,
+// read + write) sector requests, and the TMA load latency of the NEXT tile's mainloop rose from 1.6k to 2.6-4.7k clk
+// while an epilogue was draining (mainloop 8.4k clk alone, 13.8k-21k clk with a concurrent epilogue).  Here each warp
+// stages its 32 rows in a swizzled 4 KB tile and ONE elected lane moves it with a bulk tensor copy: 128-byte requests,
+// no LSU work; the fp32 residual stream is updated by a bulk reduce-add (no read at all).
+struct EpiTma {
+  const CUtensorMap* tm;
+  uint32_t stg;        // shared address of this warp's staging tile (1024-B aligned)
+  uint8_t* stg_ptr;
+};
+
+// store this warp's 32 rows x 64 bf16 columns starting at column col
+__device__ __forceinline__ void epi_tma_store(const GemmDesc& d, const EpiTma& e, const TileCoord& c, int q, int col) {
+  if (d.a_mode == 1) {
+    const int r0 = q * 32;
+    const int yy = r0 / d.bw, xx = r0 - yy * d.bw;
+    tma_store_4d(e.tm, e.stg_ptr, col, c.x0 + xx, c.y0 + yy, c.img);
+  } else {
+    tma_store_2d(e.tm, e.stg_ptr, col, c.m0 + q * 32);
+  }
+}
+
+__device__ __forceinline__ void epi_act(const GemmDesc& d, float (&f)[32]) {
+  if (d.act == PF_ACT_RELU) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.0f);
+  } else if (d.act == PF_ACT_GELU) {
+#pragma unroll
+    for (int j = 0; j < 32; j += 2) gelu_erf2(f[j], f[j + 1]);
+  } else if (d.act == PF_ACT_SOFTPLUS) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) f[j] = softplus(f[j]);
+  }
+}
+// acc + bias for 32 columns starting at logical column lcol (columns >= n_logical read no bias; TMA clips them)
+__device__ __forceinline__ void epi_bias(const GemmDesc& d, const uint32_t (&v)[32], int lcol, float (&f)[32]) {
+#pragma unroll
+  for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+  if (d.bias == nullptr) return;
+  if (lcol + 32 <= d.n_logical) {
+    const float4* bp = reinterpret_cast<const float4*>(d.bias + lcol);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float4 b = __ldg(bp + j);
+      f[4 * j] += b.x; f[4 * j + 1] += b.y; f[4 * j + 2] += b.z; f[4 * j + 3] += b.w;
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) if (lcol + j < d.n_logical) f[j] += __ldg(d.bias + lcol + j);
+  }
+}
+
+// bf16 output: groups of 64 columns (128-byte row segments); the two warps of a quadrant take alternate groups
+__device__ __forceinline__ void epilogue_tile_tma_bf16(const GemmDesc& d, EpiTma& e, uint32_t taddr, int half,
+                                                       const TileCoord& c, int q, int lane) {
+  const int ng = d.block_n >> 6;
+  for (int g = half; g < ng; g += 2) {
+    const int lcol = c.n0 + g * 64;
+    if (lcol >= d.n_logical) break;
+    uint32_t v0[32], v1[32];
+    tmem_ld32(taddr + g * 64, v0);
+    tmem_ld32(taddr + g * 64 + 32, v1);
+    tmem_ld_wait();
+    float f0[32], f1[32];
+    epi_bias(d, v0, lcol, f0);
+    epi_bias(d, v1, lcol + 32, f1);
+    epi_act(d, f0);
+    epi_act(d, f1);
+    if (lane == 0) bulk_wait_read0();                      // the previous copy has finished reading the staging tile
+    __syncwarp();
+    const uint32_t row = e.stg + lane * 128;
+    const int sw = lane & 7;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      st_shared_v4(row + ((j ^ sw) << 4), pack_bf16(f0[8 * j], f0[8 * j + 1]), pack_bf16(f0[8 * j + 2], f0[8 * j + 3]),
+                   pack_bf16(f0[8 * j + 4], f0[8 * j + 5]), pack_bf16(f0[8 * j + 6], f0[8 * j + 7]));
+      st_shared_v4(row + (((j + 4) ^ sw) << 4), pack_bf16(f1[8 * j], f1[8 * j + 1]), pack_bf16(f1[8 * j + 2], f1[8 * j + 3]),
+                   pack_bf16(f1[8 * j + 4], f1[8 * j + 5]), pack_bf16(f1[8 * j + 6], f1[8 * j + 7]));
+    }
+    fence_proxy_async_smem();
+    __syncwarp();
+    if (lane == 0) { epi_tma_store(d, e, c, q, d.out_col0 + lcol); bulk_commit(); }
+  }
+}
+
+// fp32 output (a_mode 0): chunks of 32 columns (128-byte row segments).  The residual-stream update x += gamma * (acc +
+// bias) stages gamma * (acc + bias) and lets the copy engine ADD it into x (cp.reduce.async.bulk.tensor .add.f32,
+// performed in the L2): the SM never reads x.  Each element is updated by exactly one tile: deterministic.
+__device__ __forceinline__ void epilogue_tile_tma_f32(const GemmDesc& d, EpiTma& e, uint32_t taddr, int half,
+                                                      const TileCoord& c, int q, int lane) {
+  const int nchunks = d.block_n >> 5;
+  for (int ch = half; ch < nchunks; ch += 2) {
+    const int lcol = c.n0 + ch * 32;
+    if (lcol >= d.n_logical) break;
+    uint32_t v[32];
+    tmem_ld32(taddr + ch * 32, v);
+    tmem_ld_wait();
+    float f[32];
+    epi_bias(d, v, lcol, f);
+    epi_act(d, f);
+    if (d.gamma != nullptr) {
+      if (lcol + 32 <= d.n_logical) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float4 g = __ldg(reinterpret_cast<const float4*>(d.gamma + lcol) + j);
+          f[4 * j] *= g.x; f[4 * j + 1] *= g.y; f[4 * j + 2] *= g.z; f[4 * j + 3] *= g.w;
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) f[j] = lcol + j < d.n_logical ? f[j] * __ldg(d.gamma + lcol + j) : 0.f;
+      }
+    }
+    if (lane == 0) bulk_wait_read0();                      // the previous copy has finished reading the staging tile
+    __syncwarp();
+    const uint32_t row = e.stg + lane * 128;
+    const int sw = lane & 7;
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      st_shared_v4(row + ((j ^ sw) << 4), __float_as_uint(f[4 * j]), __float_as_uint(f[4 * j + 1]),
+                   __float_as_uint(f[4 * j + 2]), __float_as_uint(f[4 * j + 3]));
+    fence_proxy_async_smem();
+    __syncwarp();
+    if (lane == 0) {
+      if (d.gamma != nullptr) tma_reduce_add_2d(e.tm, e.stg_ptr, d.out_col0 + lcol, c.m0 + q * 32);
+      else tma_store_2d(e.tm, e.stg_ptr, d.out_col0 + lcol, c.m0 + q * 32);
+      bulk_commit();
+    }
+  }
+}
+
 // Epilogue warps (4 warps, TMEM lane quadrant = warp & 3): drain accumulator stage `acc` of each tile this CTA owns.
 // Tile schedule.  Plain: CTA b takes tiles b, b + grid, ...  Multicast pairs (MC): cluster c takes tile PAIRS c, c + clusters, ...
 // where pair p = (m-tile pair p / n_tiles, n-tile p % n_tiles) and the CTA of cluster rank r owns m-tile 2 * mp + r
@@ -322,11 +491,13 @@ __device__ __forceinline__ TileIter make_iter(const GemmDesc& d, int total_tiles
 
 __device__ __forceinline__ void epilogue_loop(const GemmDesc& d, const TileIter& it, uint64_t* tmem_full,
                                               uint64_t* tmem_empty, uint32_t tmem_base, int warp, int lane,
-                                              float* tail_smem) {
+                                              float* tail_smem, EpiTma* et = nullptr) {
   const int q = warp & 3;                 // TMEM lane quadrant this warp may access
   const int half = warp >> 2;             // which of the quadrant's two warps: takes every other 32-column chunk
   const int r = q * 32 + lane;            // accumulator row owned by this thread
   int acc = 0; uint32_t acc_phase = 0;
+  GEMM_TRACE_DECL
+  const bool tr = lane == 0 && (warp == 0 || warp == 4);
   for (int ti = it.first; ti < it.count; ti += it.step) {
     TileCoord c = decode_tile(d, it.tile(ti));
     // ---- row mapping
@@ -354,9 +525,22 @@ __device__ __forceinline__ void epilogue_loop(const GemmDesc& d, const TileIter&
       int y = rem / d.W, x = rem - y * d.W;
       orow = (static_cast<long long>(img) * d.H * d.ps + y * d.ps + ky) * (d.W * d.ps) + x * d.ps + kx;
     }
+    if (tr) GEMM_TRACE(2 + half, ti, 0);
+    // TMA epilogue for this tile?  (the V^T tiles of the fused qkv projection keep the transposing direct store)
+    const bool tma_tile = et != nullptr && d.tma_out != 0 && !(d.vt != nullptr && c.n0 >= d.vt_col0);
     mbar_wait(&tmem_full[acc], acc_phase);
     tc_fence_after();
+    if (tr) GEMM_TRACE(2 + half, ti, 1);
     const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * d.block_n;
+    if (tma_tile) {
+      if (d.tma_out == 1) epilogue_tile_tma_bf16(d, *et, taddr, half, c, q, lane);
+      else epilogue_tile_tma_f32(d, *et, taddr, half, c, q, lane);
+      tc_fence_before();
+      mbar_arrive(&tmem_empty[acc]);
+      if (tr) GEMM_TRACE(2 + half, ti, 2);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      continue;
+    }
     float y2[kMaxTail];
 #pragma unroll
     for (int i = 0; i < kMaxTail; ++i) y2[i] = 0.f;
@@ -394,8 +578,10 @@ __device__ __forceinline__ void epilogue_loop(const GemmDesc& d, const TileIter&
     }
     tc_fence_before();
     mbar_arrive(&tmem_empty[acc]);
+    if (tr) GEMM_TRACE(2 + half, ti, 2);
     if (++acc == 2) { acc = 0; acc_phase ^= 1; }
   }
+  if (et != nullptr && lane == 0) bulk_wait0();    // the staging tiles are read (and the writes performed) before the CTA retires
 }
 
 // MC = true: launched as clusters of 2 CTAs that take two m-tiles of the SAME n-tile; each CTA fetches half of the
@@ -410,12 +596,13 @@ __global__ void __launch_bounds__(kGemmThreads, 1) pf_gemm_kernel(const __grid_c
   const int stages = P.stages;
   const int b_tile_bytes = d.block_n * kBlockK * 2;
   const int stage_bytes = kATileBytes + b_tile_bytes;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + stages * stage_bytes);
+  uint8_t* epi_stage = smem + stages * stage_bytes;            // [kEpiWarps][4 KB], 1024-B aligned (stage sizes are 4 KB multiples)
+  float* tail_smem = reinterpret_cast<float*>(epi_stage);      // [128][kMaxTail]: fused-tail launches never stage
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(epi_stage + kEpiStageBytes);
   uint64_t* empty_bar = full_bar + stages;
   uint64_t* tmem_full = empty_bar + stages;   // [2]
   uint64_t* tmem_empty = tmem_full + 2;       // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
-  float* tail_smem = reinterpret_cast<float*>(tmem_slot + 4);   // [128][kMaxTail]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -427,6 +614,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) pf_gemm_kernel(const __grid_c
     // a multicast stage is refilled only after BOTH CTAs' MMAs released it: two arrivals per phase
     for (int s = 0; s < stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], MC ? 2 : 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], kEpiWarps * 32); }
+    if (d.tma_out) prefetch_tmap(&P.tmOut);
     fence_barrier_init();
   }
   if (warp == kMmaWarp) tmem_alloc(tmem_slot, 512);
@@ -440,10 +628,14 @@ __global__ void __launch_bounds__(kGemmThreads, 1) pf_gemm_kernel(const __grid_c
 
   if (warp == kTmaWarp) {
     // ===================== TMA producer =====================
-    if (lane == 0) {
+    // whole warp in uniform control flow (coordinates and stage counters in uniform registers), one elected lane issues
+    {
       int stage = 0; uint32_t phase = 0;
+      GEMM_TRACE_DECL
+      if (lane == 0) GEMM_TRACE(0, 0, 9);
       for (int ti = it.first; ti < it.count; ti += it.step) {
         TileCoord c = decode_tile(d, it.tile(ti));
+        if (lane == 0) GEMM_TRACE(0, ti, 0);
         int kb = 0;  // running 64-wide K block index into the packed weights
         for (int s = 0; s < d.num_src; ++s) {
           for (int tap = 0; tap < d.taps; ++tap) {
@@ -451,17 +643,20 @@ __global__ void __launch_bounds__(kGemmThreads, 1) pf_gemm_kernel(const __grid_c
             int dx = d.taps == 9 ? tap % 3 - 1 : 0;
             for (int ch = 0; ch < d.chunks[s]; ++ch, ++kb) {
               mbar_wait(&empty_bar[stage], phase ^ 1);
+              if (lane == 0 && ti == it.first + it.step) GEMM_TRACE(0, ti, 100 + kb);
               uint8_t* sa = smem + stage * stage_bytes;
               uint8_t* sb = sa + kATileBytes;
-              mbar_expect_tx(&full_bar[stage], stage_bytes);
-              if (d.a_mode == 0) tma_load_2d(sa, &P.tmA[s], &full_bar[stage], ch * kBlockK, c.m0);
-              else tma_load_4d(sa, &P.tmA[s], &full_bar[stage], ch * kBlockK, c.x0 + dx, c.y0 + dy, c.img);
-              if (MC) {
-                const int half_rows = d.block_n >> 1;
-                tma_load_2d_mc(sb + it.rank * half_rows * 128, &P.tmBh, &full_bar[stage], kb * kBlockK,
-                               c.n0 + it.rank * half_rows, static_cast<uint16_t>(3));
-              } else {
-                tma_load_2d(sb, &P.tmB, &full_bar[stage], kb * kBlockK, c.n0);
+              if (elect_one()) {
+                mbar_expect_tx(&full_bar[stage], stage_bytes);
+                if (d.a_mode == 0) tma_load_2d(sa, &P.tmA[s], &full_bar[stage], ch * kBlockK, c.m0);
+                else tma_load_4d(sa, &P.tmA[s], &full_bar[stage], ch * kBlockK, c.x0 + dx, c.y0 + dy, c.img);
+                if (MC) {
+                  const int half_rows = d.block_n >> 1;
+                  tma_load_2d_mc(sb + it.rank * half_rows * 128, &P.tmBh, &full_bar[stage], kb * kBlockK,
+                                 c.n0 + it.rank * half_rows, static_cast<uint16_t>(3));
+                } else {
+                  tma_load_2d(sb, &P.tmB, &full_bar[stage], kb * kBlockK, c.n0);
+                }
               }
               if (++stage == stages) { stage = 0; phase ^= 1; }
             }
@@ -471,36 +666,63 @@ __global__ void __launch_bounds__(kGemmThreads, 1) pf_gemm_kernel(const __grid_c
     }
   } else if (warp == kMmaWarp) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
-      const uint32_t idesc = umma_idesc_bf16(kBlockM, d.block_n);
+    // whole warp in uniform control flow, one elected lane issues (see pf_conv3_halo_kernel)
+    {
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
+      GEMM_TRACE_DECL
       for (int ti = it.first; ti < it.count; ti += it.step) {
+        if (lane == 0) GEMM_TRACE(1, ti, 0);
+        // the last n-tile issues only the columns that exist (rounded to the MMA granule of 16): N = 544 runs as
+        // 192 + 192 + 160 instead of 3 x 192
+        const uint32_t idesc = umma_idesc_bf16(kBlockM, tile_n_eff(d, it.tile(ti)));
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         tc_fence_after();
+        if (lane == 0) GEMM_TRACE(1, ti, 1);
         const uint32_t tmem_d = tmem_base + acc * d.block_n;
-        for (int ks = 0; ks < P.k_steps; ++ks) {
-          mbar_wait(&full_bar[stage], phase);
-          tc_fence_after();
-          const uint32_t sa = smem_u32(smem + stage * stage_bytes);
-          const uint64_t adesc = umma_desc_k128(sa);
-          const uint64_t bdesc = umma_desc_k128(sa + kATileBytes);
+        uint32_t accum = 0;
+        for (int s = 0; s < d.num_src; ++s) {
+          const int nch = d.chunks[s];
+          const int nk_last = last_chunk_k16(d, s);        // K16 steps of the zero-padded last 64-channel chunk
+          for (int tap = 0; tap < d.taps; ++tap) {
+            for (int ch = 0; ch < nch; ++ch) {
+              const int nk = ch == nch - 1 ? nk_last : kBlockK / 16;
+              mbar_wait(&full_bar[stage], phase);
+              tc_fence_after();
+              if (lane == 0 && !accum) GEMM_TRACE(1, ti, 2);
+              if (lane == 0 && ti == it.first + it.step) GEMM_TRACE(1, ti, 100 + stage);
+              const uint32_t sa = smem_u32(smem + stage * stage_bytes);
+              const uint64_t adesc = umma_desc_k128(sa);
+              const uint64_t bdesc = umma_desc_k128(sa + kATileBytes);
+              if (elect_one()) {
+                if (nk == kBlockK / 16) {
 #pragma unroll
-          for (int k = 0; k < kBlockK / 16; ++k) {
-            // advance 16 bf16 = 32 B along K inside the 128-B swizzle row: +2 in the (addr>>4) field
-            umma_bf16(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (ks | k) != 0);
+                  for (int k = 0; k < kBlockK / 16; ++k)
+                    // advance 16 bf16 = 32 B along K inside the 128-B swizzle row: +2 in the (addr>>4) field
+                    umma_bf16(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, accum | k);
+                } else {
+#pragma unroll
+                  for (int k = 0; k < kBlockK / 16; ++k)
+                    if (k < nk) umma_bf16(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, accum | k);
+                }
+                if (MC) umma_commit_mc(&empty_bar[stage], static_cast<uint16_t>(3));   // release the stage in both CTAs
+                else umma_commit(&empty_bar[stage]);       // frees this smem stage once the MMAs above retire
+              }
+              accum = 1;
+              if (++stage == stages) { stage = 0; phase ^= 1; }
+            }
           }
-          if (MC) umma_commit_mc(&empty_bar[stage], static_cast<uint16_t>(3));   // release the stage in both CTAs
-          else umma_commit(&empty_bar[stage]);       // frees this smem stage once the MMAs above retire
-          if (++stage == stages) { stage = 0; phase ^= 1; }
         }
-        umma_commit(&tmem_full[acc]);                // accumulator complete -> epilogue
+        if (elect_one()) umma_commit(&tmem_full[acc]);     // accumulator complete -> epilogue
+        if (lane == 0) GEMM_TRACE(1, ti, 3);
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
   } else if (warp < kEpiWarps) {
     // ===================== epilogue (warps 0..7) =====================
-    epilogue_loop(d, it, tmem_full, tmem_empty, tmem_base, warp, lane, tail_smem);
+    EpiTma et;
+    et.tm = &P.tmOut; et.stg_ptr = epi_stage + warp * kStageTile; et.stg = smem_u32(et.stg_ptr);
+    epilogue_loop(d, it, tmem_full, tmem_empty, tmem_base, warp, lane, tail_smem, &et);
   }
 
   tc_fence_before();
@@ -530,9 +752,11 @@ constexpr int kHaloSlots = 3;
 
 // KC consecutive taps (tap0 .. tap0+KC-1) of one 64-channel chunk: 4 MMAs (K = 16 each) per tap.  `tap0` is a
 // literal at every call site, so all A offsets fold to immediates.
-template <int KC>
+// full 64-channel chunks take the lean fully unrolled path; only a source's zero-padded last chunk takes the counted one
+#define PF_ISSUE(KC, ...) do { if (nk == kBlockK / 16) issue_taps<KC, true>(__VA_ARGS__); else issue_taps<KC, false>(__VA_ARGS__); } while (0)
+template <int KC, bool FULLK>
 __device__ __forceinline__ void issue_taps(uint32_t tmem_d, uint64_t a_hi, uint32_t a_lo, uint64_t b_hi, uint32_t b_lo,
-                                           uint32_t b_tile16, int tap0, uint32_t idesc, uint32_t& first) {
+                                           uint32_t b_tile16, int tap0, uint32_t idesc, uint32_t first, int nk) {
 #pragma unroll
   for (int j = 0; j < KC; ++j) {
     const int tap = tap0 + j;
@@ -541,8 +765,10 @@ __device__ __forceinline__ void issue_taps(uint32_t tmem_d, uint64_t a_hi, uint3
     const uint32_t bl = b_lo + j * b_tile16;
 #pragma unroll
     for (int k = 0; k < kBlockK / 16; ++k) {
-      umma_bf16(tmem_d, a_hi | (al + 2 * k), b_hi | (bl + 2 * k), idesc, first ? 0u : 1u);
-      first = 0;
+      if (FULLK || k < nk) {
+        umma_bf16(tmem_d, a_hi | (al + 2 * k), b_hi | (bl + 2 * k), idesc, first ? 0u : 1u);
+        first = 0;
+      }
     }
   }
 }
@@ -585,93 +811,110 @@ __global__ void __launch_bounds__(kGemmThreads, 1) pf_conv3_halo_kernel(const __
   pdl_wait();                       // predecessor's results are visible from here on
 
   if (warp == kTmaWarp) {
-    if (lane == 0) {
-      int as = 0; uint32_t aph = 0;
-      int bs = 0; uint32_t bph = 0;
-      for (int t = blockIdx.x; t < P.total_tiles; t += gridDim.x) {
-        TileCoord c = decode_tile(d, t);
-        int kbase = 0;                                       // first 64-wide K block of this source in the weights
-        for (int s = 0; s < d.num_src; ++s) {
-          const int nch = d.chunks[s];
-          for (int ch = 0; ch < nch; ++ch) {
-            mbar_wait(&a_empty[as], aph ^ 1);
+    // whole warp in uniform control flow, one elected lane issues the copies
+    int as = 0; uint32_t aph = 0;
+    int bs = 0; uint32_t bph = 0;
+    for (int t = blockIdx.x; t < P.total_tiles; t += gridDim.x) {
+      TileCoord c = decode_tile(d, t);
+      int kbase = 0;                                       // first 64-wide K block of this source in the weights
+      for (int s = 0; s < d.num_src; ++s) {
+        const int nch = d.chunks[s];
+        for (int ch = 0; ch < nch; ++ch) {
+          mbar_wait(&a_empty[as], aph ^ 1);
+          if (elect_one()) {
             mbar_expect_tx(&a_full[as], kHaloBytes);
             tma_load_4d(smem + as * kHaloSlot, &P.tmA[s], &a_full[as], ch * kBlockK, c.x0 - 1, c.y0 - 1, c.img);
-            if (++as == kHaloSlots) { as = 0; aph ^= 1; }
-            for (int tap0 = 0; tap0 < 9; tap0 += kc) {
-              mbar_wait(&b_empty[bs], bph ^ 1);
+          }
+          if (++as == kHaloSlots) { as = 0; aph ^= 1; }
+          for (int tap0 = 0; tap0 < 9; tap0 += kc) {
+            mbar_wait(&b_empty[bs], bph ^ 1);
+            if (elect_one()) {
               mbar_expect_tx(&b_full[bs], b_stage_bytes);
               for (int j = 0; j < kc; ++j)
                 tma_load_2d(smem_b + bs * b_stage_bytes + j * b_tile_bytes, &P.tmB, &b_full[bs],
                             (kbase + (tap0 + j) * nch + ch) * kBlockK, c.n0);
-              if (++bs == stages) { bs = 0; bph ^= 1; }
             }
+            if (++bs == stages) { bs = 0; bph ^= 1; }
           }
-          kbase += 9 * nch;
         }
+        kbase += 9 * nch;
       }
     }
   } else if (warp == kMmaWarp) {
-    if (lane == 0) {
-      const uint32_t idesc = umma_idesc_bf16(kBlockM, d.block_n);
-      int as = 0; uint32_t aph = 0;
-      int bs = 0; uint32_t bph = 0;
-      int acc = 0; uint32_t acc_phase = 0;
-      for (int t = blockIdx.x; t < P.total_tiles; t += gridDim.x) {
-        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
-        tc_fence_after();
-        const uint32_t tmem_d = tmem_base + acc * d.block_n;
-        uint32_t first = 1;
-        for (int s = 0; s < d.num_src; ++s) {
-          for (int ch = 0; ch < d.chunks[s]; ++ch) {
-            mbar_wait(&a_full[as], aph);
+    // The WHOLE warp walks the loop (uniform control flow: barrier waits, descriptor arithmetic and stage counters stay
+    // in uniform registers) and one elected lane issues.  Wrapping the loop in `if (lane == 0)` instead made every
+    // tcgen05.mma pay an ELECT / R2UR.BROADCAST / BRA.U.ANY round trip (~13 instructions): with N = 32 the MMA
+    // itself is 16-32 clk, so the issue loop - not the tensor pipe - bounded those convolutions.
+    int as = 0; uint32_t aph = 0;
+    int bs = 0; uint32_t bph = 0;
+    int acc = 0; uint32_t acc_phase = 0;
+    for (int t = blockIdx.x; t < P.total_tiles; t += gridDim.x) {
+      const uint32_t idesc = umma_idesc_bf16(kBlockM, tile_n_eff(d, t));
+      mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t tmem_d = tmem_base + acc * d.block_n;
+      uint32_t first = 1;
+      for (int s = 0; s < d.num_src; ++s) {
+        const int nk_last = last_chunk_k16(d, s);
+        for (int ch = 0; ch < d.chunks[s]; ++ch) {
+          const int nk = ch == d.chunks[s] - 1 ? nk_last : kBlockK / 16;
+          mbar_wait(&a_full[as], aph);
+          tc_fence_after();
+          const uint32_t halo = smem_u32(smem + as * kHaloSlot);
+          // descriptors are (constant high word, 32-bit low word); per-tap start offsets are compile-time immediates
+          // in the fully unrolled KC variants
+          const uint64_t a_hi = (static_cast<uint64_t>(1) << 46) | (static_cast<uint64_t>(2) << 61) |
+                                (static_cast<uint64_t>((kHaloW * 128) >> 4) << 32) | (static_cast<uint64_t>(1) << 16);
+          const uint64_t b_hi = (static_cast<uint64_t>(1) << 46) | (static_cast<uint64_t>(2) << 61) |
+                                (static_cast<uint64_t>(1024 >> 4) << 32) | (static_cast<uint64_t>(1) << 16);
+          const uint32_t a_lo = (halo & 0x3FFFF) >> 4;
+          if (kc == 9) {
+            mbar_wait(&b_full[bs], bph);
             tc_fence_after();
-            const uint32_t halo = smem_u32(smem + as * kHaloSlot);
-            // Lean single-thread issue loop: descriptors are (constant high word, 32-bit low word); per-tap start
-            // offsets are compile-time immediates in the fully unrolled KC variants.  With small N the MMA itself
-            // costs ~16-64 clk, so every spare instruction in this loop shows up as lost tensor throughput.
-            const uint64_t a_hi = (static_cast<uint64_t>(1) << 46) | (static_cast<uint64_t>(2) << 61) |
-                                  (static_cast<uint64_t>((kHaloW * 128) >> 4) << 32) | (static_cast<uint64_t>(1) << 16);
-            const uint64_t b_hi = (static_cast<uint64_t>(1) << 46) | (static_cast<uint64_t>(2) << 61) |
-                                  (static_cast<uint64_t>(1024 >> 4) << 32) | (static_cast<uint64_t>(1) << 16);
-            const uint32_t a_lo = (halo & 0x3FFFF) >> 4;
-            if (kc == 9) {
+            const uint32_t b_lo = (smem_u32(smem_b + bs * b_stage_bytes) & 0x3FFFF) >> 4;
+            if (elect_one()) {
+              PF_ISSUE(9, tmem_d, a_hi, a_lo, b_hi, b_lo, b_tile_bytes >> 4, 0, idesc, first, nk);
+              umma_commit(&b_empty[bs]);
+              umma_commit(&a_empty[as]);                     // halo slot reusable once its 36 MMAs retire
+            }
+            first = 0;
+            if (++bs == stages) { bs = 0; bph ^= 1; }
+          } else if (kc == 3) {
+#pragma unroll
+            for (int g = 0; g < 3; ++g) {
               mbar_wait(&b_full[bs], bph);
               tc_fence_after();
               const uint32_t b_lo = (smem_u32(smem_b + bs * b_stage_bytes) & 0x3FFFF) >> 4;
-              issue_taps<9>(tmem_d, a_hi, a_lo, b_hi, b_lo, b_tile_bytes >> 4, 0, idesc, first);
-              umma_commit(&b_empty[bs]);
+              if (elect_one()) {
+                if (g == 0) PF_ISSUE(3, tmem_d, a_hi, a_lo, b_hi, b_lo, b_tile_bytes >> 4, 0, idesc, first, nk);
+                else if (g == 1) PF_ISSUE(3, tmem_d, a_hi, a_lo, b_hi, b_lo, b_tile_bytes >> 4, 3, idesc, first, nk);
+                else PF_ISSUE(3, tmem_d, a_hi, a_lo, b_hi, b_lo, b_tile_bytes >> 4, 6, idesc, first, nk);
+                umma_commit(&b_empty[bs]);
+                if (g == 2) umma_commit(&a_empty[as]);
+              }
+              first = 0;
               if (++bs == stages) { bs = 0; bph ^= 1; }
-            } else if (kc == 3) {
-#pragma unroll
-              for (int g = 0; g < 3; ++g) {
-                mbar_wait(&b_full[bs], bph);
-                tc_fence_after();
-                const uint32_t b_lo = (smem_u32(smem_b + bs * b_stage_bytes) & 0x3FFFF) >> 4;
-                if (g == 0) issue_taps<3>(tmem_d, a_hi, a_lo, b_hi, b_lo, b_tile_bytes >> 4, 0, idesc, first);
-                else if (g == 1) issue_taps<3>(tmem_d, a_hi, a_lo, b_hi, b_lo, b_tile_bytes >> 4, 3, idesc, first);
-                else issue_taps<3>(tmem_d, a_hi, a_lo, b_hi, b_lo, b_tile_bytes >> 4, 6, idesc, first);
-                umma_commit(&b_empty[bs]);
-                if (++bs == stages) { bs = 0; bph ^= 1; }
-              }
-            } else {
-#pragma unroll
-              for (int tap = 0; tap < 9; ++tap) {
-                mbar_wait(&b_full[bs], bph);
-                tc_fence_after();
-                const uint32_t b_lo = (smem_u32(smem_b + bs * b_stage_bytes) & 0x3FFFF) >> 4;
-                issue_taps<1>(tmem_d, a_hi, a_lo, b_hi, b_lo, 0, tap, idesc, first);
-                umma_commit(&b_empty[bs]);
-                if (++bs == stages) { bs = 0; bph ^= 1; }
-              }
             }
-            umma_commit(&a_empty[as]);                       // halo slot reusable once its 36 MMAs retire
-            if (++as == kHaloSlots) { as = 0; aph ^= 1; }
+          } else {
+#pragma unroll
+            for (int tap = 0; tap < 9; ++tap) {
+              mbar_wait(&b_full[bs], bph);
+              tc_fence_after();
+              const uint32_t b_lo = (smem_u32(smem_b + bs * b_stage_bytes) & 0x3FFFF) >> 4;
+              if (elect_one()) {
+                PF_ISSUE(1, tmem_d, a_hi, a_lo, b_hi, b_lo, 0, tap, idesc, first, nk);
+                umma_commit(&b_empty[bs]);
+                if (tap == 8) umma_commit(&a_empty[as]);
+              }
+              first = 0;
+              if (++bs == stages) { bs = 0; bph ^= 1; }
+            }
           }
+          if (++as == kHaloSlots) { as = 0; aph ^= 1; }
         }
-        umma_commit(&tmem_full[acc]);
-        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
+      if (elect_one()) umma_commit(&tmem_full[acc]);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   } else if (warp < kEpiWarps) {
     epilogue_loop(d, make_iter(d, P.total_tiles, false), tmem_full, tmem_empty, tmem_base, warp, lane, tail_smem);
@@ -690,7 +933,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) pf_conv3_halo_kernel(const __
 static int g_sm_counts[kMaxDevices] = {0};
 
 int gemm_launch(const GemmDesc& d, const CUtensorMap* tmA, const CUtensorMap& tmB, const CUtensorMap* tmBh,
-                cudaStream_t stream) {
+                const CUtensorMap* tmOut, cudaStream_t stream) {
   static bool attr_done[kMaxDevices] = {false};
   const int kMaxSmem = 227 * 1024;
   const int dev = current_device();
@@ -719,10 +962,12 @@ int gemm_launch(const GemmDesc& d, const CUtensorMap* tmA, const CUtensorMap& tm
   for (int s = d.num_src; s < 3; ++s) P.tmA[s] = tmA[0];
   P.tmB = tmB;
   P.tmBh = tmBh ? *tmBh : tmB;
+  P.tmOut = tmOut ? *tmOut : tmB;
   P.d = d;
+  if (d.tma_out && !tmOut) return set_error("gemm: tma_out without an output tensor map");
   P.kc = 1;
   int stage_bytes = kATileBytes + d.block_n * kBlockK * 2;
-  int budget = kMaxSmem - 1024 /*align*/ - kTailBytes /*barriers + fused-tail scratch*/;
+  int budget = kMaxSmem - 1024 /*align*/ - kEpiSmemBytes /*barriers + epilogue staging (aliases the fused-tail scratch)*/;
   int stages = budget / stage_bytes;
   if (stages > 8) stages = 8;
   if (stages < 2) return set_error("gemm: not enough shared memory for 2 stages");
@@ -733,7 +978,7 @@ int gemm_launch(const GemmDesc& d, const CUtensorMap* tmA, const CUtensorMap& tm
   P.total_tiles = d.m_tiles * d.n_tiles;
   if (P.total_tiles <= 0 || ks <= 0) return set_error("gemm: empty problem");
   int grid = P.total_tiles < g_sm_count ? P.total_tiles : g_sm_count;
-  size_t smem = 1024 + static_cast<size_t>(stages) * stage_bytes + kTailBytes;
+  size_t smem = 1024 + static_cast<size_t>(stages) * stage_bytes + kEpiSmemBytes;
   if (d.halo) {
     int b_bytes = d.block_n * kBlockK * 2;
     int hb = kMaxSmem - 1024 - kTailBytes - kHaloSlots * kHaloSlot;
@@ -774,5 +1019,16 @@ int gemm_launch(const GemmDesc& d, const CUtensorMap* tmA, const CUtensorMap& tm
   count_launch(d.halo ? "pf_conv3_halo_kernel" : "pf_gemm_kernel");
   return 0;
 }
+
+#ifdef PF_GEMM_TRACE
+extern "C" int pf_gemm_trace_read(unsigned long long* out) {
+  cudaDeviceSynchronize();
+  return cudaMemcpyFromSymbol(out, g_gemm_trace, sizeof(g_gemm_trace)) == cudaSuccess ? 0 : 1;
+}
+extern "C" int pf_gemm_trace_clear() {
+  static unsigned long long z[4 * 256 * 2] = {0};
+  return cudaMemcpyToSymbol(g_gemm_trace, z, sizeof(z)) == cudaSuccess ? 0 : 1;
+}
+#endif
 
 }  // namespace pf

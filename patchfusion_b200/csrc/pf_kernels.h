@@ -36,6 +36,7 @@ struct GemmDesc {
   int n2, act2, skip_main;
   float* out3;
   int out3_ld;
+  int tma_out;           // pf_gemm_kernel epilogue through shared memory + TMA: 0 direct, 1 bf16 output, 2 fp32 output / residual stream
 };
 
 int set_error(const char* fmt, ...);
@@ -69,12 +70,15 @@ void note_work(double flops, const char* fmt, ...);
 int check_launch(const char* what);
 
 // tmBh != nullptr selects the weight-multicast variant (clusters of 2 CTAs): a {64, block_n / 2} box map of the weights
+// tmOut: output tensor map when d.tma_out != 0
 int gemm_launch(const GemmDesc& d, const CUtensorMap* tmA, const CUtensorMap& tmB, const CUtensorMap* tmBh,
-                cudaStream_t stream);
+                const CUtensorMap* tmOut, cudaStream_t stream);
 
 // Tensor maps (driver entry point fetched at run time; cached by key).
 int tmap_2d_bf16(CUtensorMap* out, const void* ptr, uint64_t cols, uint64_t rows, uint64_t ld_elems, uint32_t box_cols,
                  uint32_t box_rows);
+int tmap_2d_f32(CUtensorMap* out, const void* ptr, uint64_t cols, uint64_t rows, uint64_t ld_elems, uint32_t box_cols,
+                uint32_t box_rows);
 int tmap_3d_bf16(CUtensorMap* out, const void* ptr, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t ld1_elems,
                  uint64_t ld2_elems, uint32_t b0, uint32_t b1, uint32_t b2);
 int tmap_4d_nhwc_bf16(CUtensorMap* out, const void* ptr, uint64_t C, uint64_t W, uint64_t H, uint64_t N,
