@@ -36,6 +36,15 @@ long long pf_launch_count(void);
 /* Per-launch profiler: between start and stop every kernel this library launches on `stream` is bracketed by CUDA
  * events (duration i = event i - event i-1).  pf_profile_stop returns the record count; pf_profile_get returns a
  * record's kernel name, shape label, algorithmic flops (0 for HBM kernels) and milliseconds. */
+/* Tuning switches (defaults in parentheses; each is also read once from the environment variable of the same name):
+ *   PF_OPT_TMA_EPILOGUE (1)   pf_gemm_kernel epilogue through shared memory + bulk tensor stores / reduce-add
+ *   PF_OPT_HALO_MULTICAST (1) pf_conv3_halo_kernel in clusters of 2 CTAs sharing the weight tiles by TMA multicast
+ *   PF_OPT_GEMM_MULTICAST (1) the same for the linear layers of pf_gemm_kernel
+ * Changing one invalidates nothing inside the library; callers holding CUDA graphs must re-capture. */
+#define PF_OPT_TMA_EPILOGUE 0
+#define PF_OPT_HALO_MULTICAST 1
+#define PF_OPT_GEMM_MULTICAST 2
+int pf_set_option(int32_t option, int32_t value);
 int pf_profile_start(void* stream);
 int pf_profile_stop(void);
 int pf_profile_get(int32_t i, const char** name, const char** label, double* flops, float* ms);

@@ -54,6 +54,20 @@ void count_launch(const char* name) {
     g_next_flops = 0.0; g_next_label[0] = 0;
   }
 }
+// tuning switches: -1 = not read yet (first use reads the environment variable of the same name)
+static std::atomic<int> g_opt[3] = {{-1}, {-1}, {-1}};
+int option(int which) {
+  static const char* names[3] = {"PF_OPT_TMA_EPILOGUE", "PF_OPT_HALO_MULTICAST", "PF_OPT_GEMM_MULTICAST"};
+  static const int defaults[3] = {1, 1, 1};
+  if (which < 0 || which > 2) return 0;
+  int v = g_opt[which].load(std::memory_order_relaxed);
+  if (v < 0) {
+    const char* e = getenv(names[which]);
+    v = e ? (e[0] != '0') : defaults[which];
+    g_opt[which].store(v, std::memory_order_relaxed);
+  }
+  return v;
+}
 bool pdl_enabled() {
   // opt-in (PF_B200_PDL=1): measured neutral inside CUDA graphs on B200, so the default stays the plain launch
   static const bool on = getenv("PF_B200_PDL") != nullptr && getenv("PF_B200_PDL")[0] == '1';
@@ -224,6 +238,12 @@ const char* pf_last_error(void) { return g_err; }
 int pf_version(void) { return 100; }
 long long pf_launch_count(void) { return g_launches.load(); }
 
+int pf_set_option(int32_t which, int32_t value) {
+  if (which < 0 || which > 2) return set_error("pf_set_option: unknown option %d", which);
+  g_opt[which].store(value ? 1 : 0, std::memory_order_relaxed);
+  return 0;
+}
+
 int pf_profile_start(void* stream) {
   for (auto& r : g_prof) cudaEventDestroy(r.ev);
   g_prof.clear();
@@ -388,15 +408,15 @@ int pf_gemm(pf_gemm_desc* u, void* stream) {
   d.vt_col0 = u->vt_col0; d.vt_seq = u->vt_seq; d.vt_seq_pad = u->vt_seq_pad; d.vt_dim = u->vt_dim;
   if (d.vt && (d.vt_col0 % bn) != 0) return set_error("pf_gemm: vt_col0 must be a multiple of block_n");
   // Linear layers with several m-tiles per n-tile are L2 -> SM bandwidth bound: pairs of CTAs share the weight tile by
-  // TMA multicast (PF_B200_NO_MULTICAST=1 disables).  Needs an even split of the n-tile into 1024-B aligned halves.
-  static const bool no_mc = getenv("PF_B200_NO_MULTICAST") != nullptr;
-  const bool mc = !no_mc && !halo && u->a_mode == 0 && d.ps == 1 && bn % 16 == 0 && d.m_tiles >= 4 &&
-                  static_cast<long long>(d.m_tiles) * d.n_tiles >= 148;
+  // TMA multicast (PF_OPT_GEMM_MULTICAST / PF_OPT_HALO_MULTICAST).  Needs an even split of the n-tile into 1024-B aligned halves.
+  const bool mc = bn % 16 == 0 && d.m_tiles >= 4 && static_cast<long long>(d.m_tiles) * d.n_tiles >= 148 &&
+                  (halo ? option(PF_OPT_HALO_MULTICAST) != 0
+                        : (option(PF_OPT_GEMM_MULTICAST) != 0 && u->a_mode == 0 && d.ps == 1));
   CUtensorMap tmBh;
   if (mc && tmap_2d_bf16(&tmBh, u->w_ptr, u->Ktot, n_pad, u->Ktot, 64, bn / 2)) return 1;
   // Epilogue through shared memory + TMA (pf_gemm_kernel only): plain bf16 outputs in 64-column groups, fp32 outputs
-  // and the fp32 residual stream (x += gamma * v) in 32-column chunks.  PF_B200_NO_TMA_EPI=1 keeps the direct stores.
-  static const bool no_tma_epi = getenv("PF_B200_NO_TMA_EPI") != nullptr;
+  // and the fp32 residual stream (x += gamma * v) in 32-column chunks.  PF_OPT_TMA_EPILOGUE = 0 keeps the direct stores.
+  const bool no_tma_epi = option(PF_OPT_TMA_EPILOGUE) == 0;
   CUtensorMap tmOut;
   d.tma_out = 0;
   if (!no_tma_epi && !halo && d.ps == 1 && !d.w2 && !d.res1 && !d.res2 && !d.out2) {

@@ -18,6 +18,8 @@
 // Warp roles (384 threads): warps 0-7 = epilogue (TMEM -> registers -> bias / activation / residual / LayerScale ->
 // global, full 32-B sectors per access), warp 10 = TMA producer, warp 11 = TMEM owner + single-thread tcgen05.mma issuer.
 // Two TMEM accumulator stages let the epilogue of tile i overlap the MMAs of tile i+1.
+#include <stdlib.h>
+
 #include "pf_common.cuh"
 #include "pf_kernels.h"
 
@@ -506,7 +508,7 @@ __device__ __forceinline__ void epilogue_loop(const GemmDesc& d, const TileIter&
     if (d.a_mode == 1) {
       int yy = r / d.bw, xx = r - yy * d.bw;
       int y = c.y0 + yy, x = c.x0 + xx;
-      row_ok = (y < d.H) && (x < d.W);
+      row_ok = (y < d.H) && (x < d.W) && (c.img < d.NB);     // img >= NB: the phantom tile that pairs an odd last m-tile
       orow = (static_cast<long long>(c.img) * d.H + y) * d.W + x;
     } else {
       int m = c.m0 + r;
@@ -754,6 +756,11 @@ constexpr int kHaloSlots = 3;
 // literal at every call site, so all A offsets fold to immediates.
 // full 64-channel chunks take the lean fully unrolled path; only a source's zero-padded last chunk takes the counted one
 #define PF_ISSUE(KC, ...) do { if (nk == kBlockK / 16) issue_taps<KC, true>(__VA_ARGS__); else issue_taps<KC, false>(__VA_ARGS__); } while (0)
+template <bool MC>
+__device__ __forceinline__ void halo_release_b(uint64_t* bar) {
+  if (MC) umma_commit_mc(bar, static_cast<uint16_t>(3));    // the weight stage is free in both CTAs of the pair
+  else umma_commit(bar);
+}
 template <int KC, bool FULLK>
 __device__ __forceinline__ void issue_taps(uint32_t tmem_d, uint64_t a_hi, uint32_t a_lo, uint64_t b_hi, uint32_t b_lo,
                                            uint32_t b_tile16, int tap0, uint32_t idesc, uint32_t first, int nk) {
@@ -773,6 +780,11 @@ __device__ __forceinline__ void issue_taps(uint32_t tmem_d, uint64_t a_hi, uint3
   }
 }
 
+// MC = true: clusters of 2 CTAs take two m-tiles (pixel tiles) of the SAME n-tile; each CTA fetches half of the rows of
+// every weight tile and multicasts it into both CTAs.  The weights are ~90 % of this kernel's L2 -> SM traffic (one
+// 23 KB halo against nine 16-32 KB tap tiles per 64-channel chunk) and that traffic sits at the fabric's ceiling
+// (~46 B/clk/SM measured on the linear layers), so halving it is what the N = 32 layers and the partial chunks need.
+template <bool MC>
 __global__ void __launch_bounds__(kGemmThreads, 1) pf_conv3_halo_kernel(const __grid_constant__ GemmKernelParams P) {
   extern __shared__ uint8_t smem_raw[];
   const GemmDesc& d = P.d;
@@ -799,23 +811,26 @@ __global__ void __launch_bounds__(kGemmThreads, 1) pf_conv3_halo_kernel(const __
     for (int s = 0; s < d.num_src; ++s) prefetch_tmap(&P.tmA[s]);
     prefetch_tmap(&P.tmB);
     for (int s = 0; s < kHaloSlots; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
-    for (int s = 0; s < stages; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
+    // a multicast weight stage is refilled only after BOTH CTAs' MMAs released it: two arrivals per phase
+    for (int s = 0; s < stages; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], MC ? 2 : 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], kEpiWarps * 32); }
     fence_barrier_init();
   }
   if (warp == kMmaWarp) tmem_alloc(tmem_slot, 512);
   tc_fence_before();
   __syncthreads();
+  if (MC) cluster_sync_all();       // the peer's barriers exist before anything is multicast into its shared memory
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  const TileIter it = make_iter(d, P.total_tiles, MC);
   pdl_wait();                       // predecessor's results are visible from here on
 
   if (warp == kTmaWarp) {
     // whole warp in uniform control flow, one elected lane issues the copies
     int as = 0; uint32_t aph = 0;
     int bs = 0; uint32_t bph = 0;
-    for (int t = blockIdx.x; t < P.total_tiles; t += gridDim.x) {
-      TileCoord c = decode_tile(d, t);
+    for (int ti = it.first; ti < it.count; ti += it.step) {
+      TileCoord c = decode_tile(d, it.tile(ti));
       int kbase = 0;                                       // first 64-wide K block of this source in the weights
       for (int s = 0; s < d.num_src; ++s) {
         const int nch = d.chunks[s];
@@ -830,9 +845,17 @@ __global__ void __launch_bounds__(kGemmThreads, 1) pf_conv3_halo_kernel(const __
             mbar_wait(&b_empty[bs], bph ^ 1);
             if (elect_one()) {
               mbar_expect_tx(&b_full[bs], b_stage_bytes);
-              for (int j = 0; j < kc; ++j)
-                tma_load_2d(smem_b + bs * b_stage_bytes + j * b_tile_bytes, &P.tmB, &b_full[bs],
-                            (kbase + (tap0 + j) * nch + ch) * kBlockK, c.n0);
+              if (MC) {
+                const int half_rows = d.block_n >> 1;
+                for (int j = 0; j < kc; ++j)
+                  tma_load_2d_mc(smem_b + bs * b_stage_bytes + j * b_tile_bytes + it.rank * half_rows * 128, &P.tmBh,
+                                 &b_full[bs], (kbase + (tap0 + j) * nch + ch) * kBlockK, c.n0 + it.rank * half_rows,
+                                 static_cast<uint16_t>(3));
+              } else {
+                for (int j = 0; j < kc; ++j)
+                  tma_load_2d(smem_b + bs * b_stage_bytes + j * b_tile_bytes, &P.tmB, &b_full[bs],
+                              (kbase + (tap0 + j) * nch + ch) * kBlockK, c.n0);
+              }
             }
             if (++bs == stages) { bs = 0; bph ^= 1; }
           }
@@ -848,8 +871,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1) pf_conv3_halo_kernel(const __
     int as = 0; uint32_t aph = 0;
     int bs = 0; uint32_t bph = 0;
     int acc = 0; uint32_t acc_phase = 0;
-    for (int t = blockIdx.x; t < P.total_tiles; t += gridDim.x) {
-      const uint32_t idesc = umma_idesc_bf16(kBlockM, tile_n_eff(d, t));
+    for (int ti = it.first; ti < it.count; ti += it.step) {
+      const uint32_t idesc = umma_idesc_bf16(kBlockM, tile_n_eff(d, it.tile(ti)));
       mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
       tc_fence_after();
       const uint32_t tmem_d = tmem_base + acc * d.block_n;
@@ -874,7 +897,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) pf_conv3_halo_kernel(const __
             const uint32_t b_lo = (smem_u32(smem_b + bs * b_stage_bytes) & 0x3FFFF) >> 4;
             if (elect_one()) {
               PF_ISSUE(9, tmem_d, a_hi, a_lo, b_hi, b_lo, b_tile_bytes >> 4, 0, idesc, first, nk);
-              umma_commit(&b_empty[bs]);
+              halo_release_b<MC>(&b_empty[bs]);
               umma_commit(&a_empty[as]);                     // halo slot reusable once its 36 MMAs retire
             }
             first = 0;
@@ -889,7 +912,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) pf_conv3_halo_kernel(const __
                 if (g == 0) PF_ISSUE(3, tmem_d, a_hi, a_lo, b_hi, b_lo, b_tile_bytes >> 4, 0, idesc, first, nk);
                 else if (g == 1) PF_ISSUE(3, tmem_d, a_hi, a_lo, b_hi, b_lo, b_tile_bytes >> 4, 3, idesc, first, nk);
                 else PF_ISSUE(3, tmem_d, a_hi, a_lo, b_hi, b_lo, b_tile_bytes >> 4, 6, idesc, first, nk);
-                umma_commit(&b_empty[bs]);
+                halo_release_b<MC>(&b_empty[bs]);
                 if (g == 2) umma_commit(&a_empty[as]);
               }
               first = 0;
@@ -903,7 +926,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) pf_conv3_halo_kernel(const __
               const uint32_t b_lo = (smem_u32(smem_b + bs * b_stage_bytes) & 0x3FFFF) >> 4;
               if (elect_one()) {
                 PF_ISSUE(1, tmem_d, a_hi, a_lo, b_hi, b_lo, 0, tap, idesc, first, nk);
-                umma_commit(&b_empty[bs]);
+                halo_release_b<MC>(&b_empty[bs]);
                 if (tap == 8) umma_commit(&a_empty[as]);
               }
               first = 0;
@@ -917,10 +940,11 @@ __global__ void __launch_bounds__(kGemmThreads, 1) pf_conv3_halo_kernel(const __
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   } else if (warp < kEpiWarps) {
-    epilogue_loop(d, make_iter(d, P.total_tiles, false), tmem_full, tmem_empty, tmem_base, warp, lane, tail_smem);
+    epilogue_loop(d, it, tmem_full, tmem_empty, tmem_base, warp, lane, tail_smem);
   }
   tc_fence_before();
   __syncthreads();
+  if (MC) cluster_sync_all();       // no CTA exits while its peer may still multicast into it / arrive on its barriers
   if (warp == kMmaWarp) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
@@ -941,7 +965,8 @@ int gemm_launch(const GemmDesc& d, const CUtensorMap* tmA, const CUtensorMap& tm
     cudaError_t e = cudaFuncSetAttribute(pf_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(pf_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
     if (e != cudaSuccess) return set_error("cudaFuncSetAttribute(pf_gemm_kernel): %s", cudaGetErrorString(e));
-    e = cudaFuncSetAttribute(pf_conv3_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
+    e = cudaFuncSetAttribute(pf_conv3_halo_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(pf_conv3_halo_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
     if (e != cudaSuccess) return set_error("cudaFuncSetAttribute(pf_conv3_halo_kernel): %s", cudaGetErrorString(e));
     cudaDeviceGetAttribute(&g_sm_counts[dev], cudaDevAttrMultiProcessorCount, dev);
     attr_done[dev] = true;
@@ -986,6 +1011,8 @@ int gemm_launch(const GemmDesc& d, const CUtensorMap* tmA, const CUtensorMap& tm
     int kc = 1;
     if (9 * b_bytes * 2 <= hb) kc = 9;
     else if (3 * b_bytes * 2 <= hb && d.block_n < 256) kc = 3;
+    static const int kc_force = getenv("PF_B200_HALO_KC") ? atoi(getenv("PF_B200_HALO_KC")) : 0;   // tuning hook
+    if ((kc_force == 1 || kc_force == 3 || kc_force == 9) && kc_force * b_bytes * 2 <= hb) kc = kc_force;
     P.kc = kc;
     b_bytes *= kc;
     int hstages = hb / b_bytes;
@@ -993,7 +1020,24 @@ int gemm_launch(const GemmDesc& d, const CUtensorMap* tmA, const CUtensorMap& tm
     if (hstages < 2) return set_error("conv3 halo: not enough shared memory");
     P.stages = hstages;
     size_t hsmem = 1024 + static_cast<size_t>(kHaloSlots) * kHaloSlot + static_cast<size_t>(hstages) * b_bytes + kTailBytes;
-    cudaError_t le = launch_pdl(pf_conv3_halo_kernel, dim3(grid), dim3(kGemmThreads), hsmem, stream, P);
+    cudaError_t le;
+    if (tmBh != nullptr) {
+      // weight-multicast pairs: clusters of 2 CTAs over (m-tile pair, n-tile) work items
+      const int pairs = ((d.m_tiles + 1) / 2) * d.n_tiles;
+      const int clusters = pairs < g_sm_count / 2 ? pairs : g_sm_count / 2;
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(2 * clusters); cfg.blockDim = dim3(kGemmThreads); cfg.dynamicSmemBytes = hsmem; cfg.stream = stream;
+      cudaLaunchAttribute at[2];
+      at[0].id = cudaLaunchAttributeClusterDimension;
+      at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+      at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      at[1].val.programmaticStreamSerializationAllowed = 1;
+      cfg.attrs = at;
+      cfg.numAttrs = pdl_enabled() ? 2 : 1;
+      le = cudaLaunchKernelEx(&cfg, pf_conv3_halo_kernel<true>, P);
+    } else {
+      le = launch_pdl(pf_conv3_halo_kernel<false>, dim3(grid), dim3(kGemmThreads), hsmem, stream, P);
+    }
     if (le != cudaSuccess) return set_error("pf_conv3_halo_kernel launch: %s", cudaGetErrorString(le));
   } else if (tmBh != nullptr) {
     // weight-multicast pairs: clusters of 2 CTAs over (m-tile pair, n-tile) work items

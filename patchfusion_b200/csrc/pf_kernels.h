@@ -49,6 +49,7 @@ inline int current_device() {
   return (d < 0 || d >= kMaxDevices) ? 0 : d;
 }
 bool pdl_enabled();
+int option(int which);          // PF_OPT_* tuning switches (pf_set_option / environment)
 
 // <<<>>> replacement that sets the programmatic-stream-serialization attribute (kernels launched through it call
 // pdl_wait() before touching global memory).

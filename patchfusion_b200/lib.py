@@ -13,6 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, os.environ.get('PF_B200_LIBNAME', 'libpf_b200.so'))
 
 ACT_NONE, ACT_RELU, ACT_GELU, ACT_SOFTPLUS = 0, 1, 2, 3
+OPT_TMA_EPILOGUE, OPT_HALO_MULTICAST, OPT_GEMM_MULTICAST = 0, 1, 2
 
 
 class PFError(RuntimeError):
@@ -43,6 +44,7 @@ class GemmDesc(C.Structure):
 _i, _f, _p, _ll = C.c_int32, C.c_float, C.c_void_p, C.c_int64
 # name -> argument types (all return int status), in the order of include/pf_b200.h
 SIGNATURES = {
+    'pf_set_option': [_i, _i],
     'pf_profile_start': [_p],
     'pf_profile_stop': [],
     'pf_profile_get': [_i, _p, _p, _p, _p],

@@ -112,7 +112,11 @@ def test_qkv_split_transposed_v(cuda):
 
 @pytest.mark.parametrize('NB,H,W,cs,N,act', [(2, 14, 19, [64], 64, 'none'), (1, 37, 50, [128], 256, 'relu'),
                                              (2, 28, 37, [32, 64, 64], 32, 'relu'), (1, 56, 74, [192], 192, 'none'),
-                                             (1, 30, 41, [8], 32, 'relu'), (3, 16, 16, [544], 544, 'relu')])
+                                             (1, 30, 41, [8], 32, 'relu'), (3, 16, 16, [544], 544, 'relu'),
+                                             # >= 148 tiles: the weight-multicast pairs of the halo kernel (even and
+                                             # odd m-tile counts, three n-tiles with a narrower last one, N = 32)
+                                             (5, 50, 70, [96], 64, 'relu'), (7, 48, 72, [40, 64], 544, 'none'),
+                                             (7, 48, 72, [136], 32, 'relu')])
 @pytest.mark.parametrize('tile', [None, (8, 16)])
 def test_conv3x3(cuda, NB, H, W, cs, N, act, tile):
     """tile=None: halo-tile kernel (one A fetch per chunk); tile=(8,16): generic per-tap TMA kernel."""
@@ -130,6 +134,19 @@ def test_conv3x3(cuda, NB, H, W, cs, N, act, tile):
     if act == 'relu':
         ref = F.relu(ref)
     check('conv3x3 %s -> %d @%dx%d' % (cs, N, H, W), from_nhwc(out, N), ref, 1e-2)
+
+
+@pytest.mark.parametrize('NB,H,W,cs,N,act', [(5, 50, 70, [96], 64, 'relu'), (7, 48, 72, [40, 64], 544, 'none'),
+                                             (7, 48, 72, [136], 32, 'relu')])
+def test_conv3x3_halo_without_weight_multicast(cuda, NB, H, W, cs, N, act):
+    """PF_OPT_HALO_MULTICAST = 0: the same >= 148-tile shapes (which take the cluster-of-2 weight-multicast variant by
+    default, see test_conv3x3) through the plain one-CTA-per-tile schedule"""
+    from patchfusion_b200 import lib
+    lib.call('pf_set_option', lib.OPT_HALO_MULTICAST, 0)
+    try:
+        test_conv3x3(cuda, NB, H, W, cs, N, act, None)
+    finally:
+        lib.call('pf_set_option', lib.OPT_HALO_MULTICAST, 1)
 
 
 def test_conv3x3_residuals_and_relu_copy(cuda):

@@ -69,4 +69,9 @@ for fam, label, fl, t in recs:
 os.makedirs('gpurun_out', exist_ok=True)
 json.dump(dict(ms_per_image=ms, tiles_per_s=49e3 / ms, by_label=by, checksum=float(y.double().sum())),
           open('gpurun_out/ab_%s.json' % tag, 'w'))
-print(tag, 'ms/image %.2f  tiles/s %.1f  checksum %.6f' % (ms, 49e3 / ms, float(y.double().sum())))
+torch.save(y.cpu(), '/tmp/ab_%s.pt' % tag)
+msg = ''
+if tag != 'base' and os.path.exists('/tmp/ab_base.pt'):
+    ref = torch.load('/tmp/ab_base.pt')
+    msg = '  max|y - base| %.3e (range %.3f..%.3f)' % (float((y.cpu() - ref).abs().max()), float(ref.min()), float(ref.max()))
+print(tag, 'ms/image %.2f  tiles/s %.1f  checksum %.6f%s' % (ms, 49e3 / ms, float(y.double().sum()), msg))
