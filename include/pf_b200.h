@@ -40,10 +40,16 @@ long long pf_launch_count(void);
  *   PF_OPT_TMA_EPILOGUE (1)   pf_gemm_kernel epilogue through shared memory + bulk tensor stores / reduce-add
  *   PF_OPT_HALO_MULTICAST (1) pf_conv3_halo_kernel in clusters of 2 CTAs sharing the weight tiles by TMA multicast
  *   PF_OPT_GEMM_MULTICAST (1) the same for the linear layers of pf_gemm_kernel
+ *   PF_OPT_FUSED_RESAMPLE (0) pf_fusion_forward: bilinear resamples feeding the U-Net's 3x3 convs are produced in the
+ *                             conv's operand stage (pf_gemm_desc.rs_h / rs_w) instead of being materialised.  Correct
+ *                             and parity-tested, but measured SLOWER on B200 (step 215 -> 317 ms): the blend costs ~3.7k
+ *                             warp-instructions per 64-channel halo chunk (bf16 <-> fp32 conversion + FFMA2) against
+ *                             3.4-4.6k clk of MMA per chunk, and only two warps of the CTA are free to produce it.
  * Changing one invalidates nothing inside the library; callers holding CUDA graphs must re-capture. */
 #define PF_OPT_TMA_EPILOGUE 0
 #define PF_OPT_HALO_MULTICAST 1
 #define PF_OPT_GEMM_MULTICAST 2
+#define PF_OPT_FUSED_RESAMPLE 3
 int pf_set_option(int32_t option, int32_t value);
 int pf_profile_start(void* stream);
 int pf_profile_stop(void);
@@ -87,6 +93,11 @@ typedef struct pf_gemm_desc {
    * act2(b2[i] + sum_j w2[i*N + j] * v[j]), i < n2 <= 16; needs N <= block_n (one N tile).  skip_main != 0
    * suppresses the main store. */
   const float* w2; const float* b2; int32_t n2, act2, skip_main; float* out3; int32_t out3_ld;
+  /* Fused bilinear resample of a 3x3 conv's input (F.interpolate(mode='bilinear', align_corners=True) feeding the
+   * conv, guided_fusion_model.py:98-99,191-203): rs_h[i] > 0 means source i is a [NB, rs_h, rs_w, a_ld] map that the
+   * conv reads THROUGH the resample to (H, W); the up-sampled tensor is never written to memory - a producer warp of
+   * the halo-tile kernel interpolates each 18 x 10 pixel halo straight into the swizzled operand tile. */
+  int32_t rs_h[3], rs_w[3];
 } pf_gemm_desc;
 
 int pf_gemm(pf_gemm_desc* desc, void* stream);

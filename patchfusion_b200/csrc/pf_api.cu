@@ -55,11 +55,11 @@ void count_launch(const char* name) {
   }
 }
 // tuning switches: -1 = not read yet (first use reads the environment variable of the same name)
-static std::atomic<int> g_opt[3] = {{-1}, {-1}, {-1}};
+static std::atomic<int> g_opt[4] = {{-1}, {-1}, {-1}, {-1}};
 int option(int which) {
-  static const char* names[3] = {"PF_OPT_TMA_EPILOGUE", "PF_OPT_HALO_MULTICAST", "PF_OPT_GEMM_MULTICAST"};
-  static const int defaults[3] = {1, 1, 1};
-  if (which < 0 || which > 2) return 0;
+  static const char* names[4] = {"PF_OPT_TMA_EPILOGUE", "PF_OPT_HALO_MULTICAST", "PF_OPT_GEMM_MULTICAST", "PF_OPT_FUSED_RESAMPLE"};
+  static const int defaults[4] = {1, 1, 1, 0};
+  if (which < 0 || which > 3) return 0;
   int v = g_opt[which].load(std::memory_order_relaxed);
   if (v < 0) {
     const char* e = getenv(names[which]);
@@ -239,7 +239,7 @@ int pf_version(void) { return 100; }
 long long pf_launch_count(void) { return g_launches.load(); }
 
 int pf_set_option(int32_t which, int32_t value) {
-  if (which < 0 || which > 2) return set_error("pf_set_option: unknown option %d", which);
+  if (which < 0 || which > 3) return set_error("pf_set_option: unknown option %d", which);
   g_opt[which].store(value ? 1 : 0, std::memory_order_relaxed);
   return 0;
 }
@@ -350,12 +350,36 @@ int pf_gemm(pf_gemm_desc* u, void* stream) {
   static const bool no_halo = getenv("PF_B200_NO_HALO") != nullptr;
   const bool halo = u->a_mode == 1 && u->taps == 9 && u->bh == 0 && u->bw == 0 && !no_halo;
   d.halo = halo ? 1 : 0;
+  bool any_rs = false;
+  for (int s = 0; s < u->num_src; ++s) {
+    if (u->rs_h[s] < 0 || u->rs_w[s] < 0 || (u->rs_h[s] > 0) != (u->rs_w[s] > 0)) return set_error("pf_gemm: bad rs_h/rs_w of source %d", s);
+    any_rs = any_rs || u->rs_h[s] > 0;
+  }
+  if (any_rs && !halo) return set_error("pf_gemm: resampled sources (rs_h > 0) need the 3x3 halo-tile path");
   if (halo) {
     d.bh = 16; d.bw = 8;
     d.tiles_y = (u->H + 15) / 16; d.tiles_x = (u->W + 7) / 8;
     d.m_tiles = u->NB * d.tiles_y * d.tiles_x;
-    for (int s = 0; s < u->num_src; ++s)
+    int first_plain = -1;
+    for (int s = 0; s < u->num_src; ++s) {
+      if (u->rs_h[s] > 0) {
+        // read through a fused bilinear resample: no tensor map, the producer warps gather from the low-resolution map
+        d.rs_ptr[s] = static_cast<const __nv_bfloat16*>(u->a_ptr[s]);
+        d.rs_h[s] = u->rs_h[s]; d.rs_w[s] = u->rs_w[s]; d.rs_ld[s] = u->a_ld[s];
+        d.rs_sy[s] = u->H > 1 ? static_cast<float>(u->rs_h[s] - 1) / static_cast<float>(u->H - 1) : 0.f;
+        d.rs_sx[s] = u->W > 1 ? static_cast<float>(u->rs_w[s] - 1) / static_cast<float>(u->W - 1) : 0.f;
+        d.rs_any = 1;
+        if (reinterpret_cast<uintptr_t>(u->a_ptr[s]) & 15) return set_error("pf_gemm: resampled source %d not 16-byte aligned", s);
+        continue;
+      }
       if (tmap_4d_nhwc_bf16(&tmA[s], u->a_ptr[s], u->a_c[s], u->W, u->H, u->NB, u->a_ld[s], 64, 10, 18)) return 1;
+      if (first_plain < 0) first_plain = s;
+    }
+    for (int s = 0; s < u->num_src; ++s)       // placeholder maps for the resampled sources (never dereferenced)
+      if (u->rs_h[s] > 0) {
+        if (first_plain >= 0) tmA[s] = tmA[first_plain];
+        else memset(&tmA[s], 0, sizeof(CUtensorMap));
+      }
   } else if (u->a_mode == 1) {
     int bh = u->bh, bw = u->bw;
     if (bh == 0 || bw == 0) choose_tile(u->H, u->W, &bh, &bw);

@@ -780,6 +780,64 @@ __device__ __forceinline__ void issue_taps(uint32_t tmem_d, uint64_t a_hi, uint3
   }
 }
 
+// ---- fused bilinear resample (align_corners=True) of a halo-kernel source -------------------------------------------
+// F.interpolate(x, (H, W), mode='bilinear', align_corners=True) feeding a 3x3 conv (guided_fusion_model.py:98-99,
+// 191-203) used to be materialised by resize_bilinear_tiled_kernel (5 % of the step, written once and read back by the
+// conv).  Instead a producer warp builds the 18 x 10 pixel halo of one 64-channel chunk directly in the swizzled
+// operand tile TMA would have written: lane -> (halo pixel, 8-channel piece), four 16-byte taps from the low-resolution
+// map (L1/L2 resident: the taps of neighbouring pixels overlap), the same FFMA2 blend and bf16 rounding as the
+// stand-alone kernel, zeros for the conv padding ring / pad channels.  Same source coordinate as ATen: scale * dst.
+constexpr int kRsWarp0 = kEpiWarps;      // warps 8, 9: resample producers (alternate chunks)
+__device__ __forceinline__ void rs_coord(int dst, int in, float scale, int& lo, int& hi, float& frac) {
+  const float src = scale * dst;
+  lo = static_cast<int>(src);
+  if (lo > in - 1) lo = in - 1;
+  hi = lo + (lo < in - 1 ? 1 : 0);
+  frac = src - lo;
+}
+__device__ __forceinline__ void halo_fill_bilinear(uint32_t slot, const GemmDesc& d, int s, int ch, const TileCoord& c, int lane) {
+  const int ih = d.rs_h[s], iw = d.rs_w[s], ld = d.rs_ld[s];
+  const __nv_bfloat16* src = d.rs_ptr[s] + static_cast<size_t>(c.img) * ih * iw * ld + ch * kBlockK;
+  const int cvalid = d.k_true[s] - ch * kBlockK;            // channels of this chunk that exist (multiple of 8)
+  const float sy = d.rs_sy[s], sx = d.rs_sx[s];
+  const int j = lane & 7;                                    // 16-byte piece (8 channels) of the pixel's 128-byte row
+  const bool jok = j * 8 < cvalid && c.img < d.NB;
+#pragma unroll 5
+  for (int p = lane >> 3; p < kHaloW * kHaloH; p += 4) {
+    const int hy = p / kHaloW, hx = p - hy * kHaloW;
+    const int Y = c.y0 - 1 + hy, X = c.x0 - 1 + hx;
+    uint32_t o0 = 0, o1 = 0, o2 = 0, o3 = 0;
+    if (jok && Y >= 0 && Y < d.H && X >= 0 && X < d.W) {
+      int y0, y1, x0, x1; float fy, fx;
+      rs_coord(Y, ih, sy, y0, y1, fy);
+      rs_coord(X, iw, sx, x0, x1, fx);
+      const __nv_bfloat16* r0 = src + static_cast<size_t>(y0) * iw * ld + j * 8;
+      const __nv_bfloat16* r1 = src + static_cast<size_t>(y1) * iw * ld + j * 8;
+      const uint4 ua = __ldg(reinterpret_cast<const uint4*>(r0 + static_cast<size_t>(x0) * ld));
+      const uint4 ub = __ldg(reinterpret_cast<const uint4*>(r0 + static_cast<size_t>(x1) * ld));
+      const uint4 uc = __ldg(reinterpret_cast<const uint4*>(r1 + static_cast<size_t>(x0) * ld));
+      const uint4 ud = __ldg(reinterpret_cast<const uint4*>(r1 + static_cast<size_t>(x1) * ld));
+      const float w00 = (1.f - fy) * (1.f - fx), w01 = (1.f - fy) * fx, w10 = fy * (1.f - fx), w11 = fy * fx;
+      const uint64_t p00 = pack2f(w00, w00), p01 = pack2f(w01, w01), p10 = pack2f(w10, w10), p11 = pack2f(w11, w11);
+      const uint32_t wa[4] = {ua.x, ua.y, ua.z, ua.w}, wb[4] = {ub.x, ub.y, ub.z, ub.w};
+      const uint32_t wc[4] = {uc.x, uc.y, uc.z, uc.w}, wd[4] = {ud.x, ud.y, ud.z, ud.w};
+      uint32_t ow[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        uint64_t r = mul2(p00, pack2(wa[k] << 16, wa[k] & 0xffff0000u));
+        r = fma2(p01, pack2(wb[k] << 16, wb[k] & 0xffff0000u), r);
+        r = fma2(p10, pack2(wc[k] << 16, wc[k] & 0xffff0000u), r);
+        r = fma2(p11, pack2(wd[k] << 16, wd[k] & 0xffff0000u), r);
+        float lo, hi;
+        unpack2f(r, lo, hi);
+        ow[k] = pack_bf16(lo, hi);
+      }
+      o0 = ow[0]; o1 = ow[1]; o2 = ow[2]; o3 = ow[3];
+    }
+    st_shared_v4(slot + p * 128 + ((j ^ (p & 7)) << 4), o0, o1, o2, o3);
+  }
+}
+
 // MC = true: clusters of 2 CTAs take two m-tiles (pixel tiles) of the SAME n-tile; each CTA fetches half of the rows of
 // every weight tile and multicasts it into both CTAs.  The weights are ~90 % of this kernel's L2 -> SM traffic (one
 // 23 KB halo against nine 16-32 KB tap tiles per 64-channel chunk) and that traffic sits at the fabric's ceiling
@@ -808,7 +866,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) pf_conv3_halo_kernel(const __
   const int lane = threadIdx.x & 31;
   pdl_launch_dependents();
   if (warp == kTmaWarp && lane == 0) {
-    for (int s = 0; s < d.num_src; ++s) prefetch_tmap(&P.tmA[s]);
+    for (int s = 0; s < d.num_src; ++s) if (d.rs_h[s] == 0) prefetch_tmap(&P.tmA[s]);
     prefetch_tmap(&P.tmB);
     for (int s = 0; s < kHaloSlots; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
     // a multicast weight stage is refilled only after BOTH CTAs' MMAs released it: two arrivals per phase
@@ -835,10 +893,12 @@ __global__ void __launch_bounds__(kGemmThreads, 1) pf_conv3_halo_kernel(const __
       for (int s = 0; s < d.num_src; ++s) {
         const int nch = d.chunks[s];
         for (int ch = 0; ch < nch; ++ch) {
-          mbar_wait(&a_empty[as], aph ^ 1);
-          if (elect_one()) {
-            mbar_expect_tx(&a_full[as], kHaloBytes);
-            tma_load_4d(smem + as * kHaloSlot, &P.tmA[s], &a_full[as], ch * kBlockK, c.x0 - 1, c.y0 - 1, c.img);
+          if (d.rs_h[s] == 0) {                            // (resampled sources: the producer warps own the slot)
+            mbar_wait(&a_empty[as], aph ^ 1);
+            if (elect_one()) {
+              mbar_expect_tx(&a_full[as], kHaloBytes);
+              tma_load_4d(smem + as * kHaloSlot, &P.tmA[s], &a_full[as], ch * kBlockK, c.x0 - 1, c.y0 - 1, c.img);
+            }
           }
           if (++as == kHaloSlots) { as = 0; aph ^= 1; }
           for (int tap0 = 0; tap0 < 9; tap0 += kc) {
@@ -938,6 +998,30 @@ __global__ void __launch_bounds__(kGemmThreads, 1) pf_conv3_halo_kernel(const __
       }
       if (elect_one()) umma_commit(&tmem_full[acc]);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  } else if (warp >= kRsWarp0 && warp < kRsWarp0 + 2) {
+    // ===================== resample producers: halo tiles of the sources read through a bilinear resample =====================
+    if (d.rs_any) {
+      int as = 0; uint32_t aph = 0;
+      int turn = 0;                                          // the two warps take alternate resampled chunks
+      for (int ti = it.first; ti < it.count; ti += it.step) {
+        TileCoord c = decode_tile(d, it.tile(ti));
+        for (int s = 0; s < d.num_src; ++s) {
+          for (int ch = 0; ch < d.chunks[s]; ++ch) {
+            if (d.rs_h[s] != 0) {
+              if ((turn & 1) == warp - kRsWarp0) {
+                mbar_wait(&a_empty[as], aph ^ 1);
+                halo_fill_bilinear(smem_u32(smem + as * kHaloSlot), d, s, ch, c, lane);
+                fence_proxy_async_smem();                    // generic-proxy writes -> visible to the tensor core's reads
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&a_full[as]);
+              }
+              ++turn;
+            }
+            if (++as == kHaloSlots) { as = 0; aph ^= 1; }
+          }
+        }
+      }
     }
   } else if (warp < kEpiWarps) {
     epilogue_loop(d, it, tmem_full, tmem_empty, tmem_base, warp, lane, tail_smem);

@@ -1,6 +1,7 @@
 // Internal declarations shared by the translation units of libpf_b200.so.
 #pragma once
 #include <cuda.h>
+#include <cuda_bf16.h>
 #include <cuda_runtime.h>
 
 #include "../../include/pf_b200.h"
@@ -36,6 +37,12 @@ struct GemmDesc {
   int n2, act2, skip_main;
   float* out3;
   int out3_ld;
+  // fused bilinear resample of halo-kernel sources (rs_h > 0): low-resolution map, its size / pitch and the
+  // align_corners scales (in - 1) / (out - 1)
+  const __nv_bfloat16* rs_ptr[3];
+  int rs_h[3], rs_w[3], rs_ld[3];
+  float rs_sy[3], rs_sx[3];
+  int rs_any;
   int tma_out;           // pf_gemm_kernel epilogue through shared memory + TMA: 0 direct, 1 bf16 output, 2 fp32 output / residual stream
 };
 

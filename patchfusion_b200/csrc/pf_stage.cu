@@ -120,6 +120,34 @@ static void conv_into(Ctx& c, const pf_layer& L, const Map* const* srcs, int ns,
   c.chk(pf_gemm(&d, c.stream));
 }
 
+// 3x3 conv whose sources are read THROUGH F.interpolate(mode='bilinear', align_corners=True) to (H, W): sources of
+// another size are resampled inside the conv kernel's operand stage (pf_gemm_desc.rs_h / rs_w) instead of being
+// materialised; sources already at (H, W) are read directly.  Opt-in (PF_OPT_FUSED_RESAMPLE = 1): two producer warps per
+// CTA cannot keep up with the tensor pipe (measured 215 -> 317 ms per 4K image), so the default materialises them.
+static Map resize(Ctx& c, const Map& x, int OH, int OW);
+static Map conv_resampled(Ctx& c, const pf_layer& L, const Map* const* srcs, int ns, int H, int W, const GemmOpt& o = GemmOpt()) {
+  Map out = c.map(srcs[0]->B, H, W, L.N);
+  if (L.taps != 9 || !option(PF_OPT_FUSED_RESAMPLE)) {
+    Map tmp[3];
+    const Map* a[3];
+    for (int i = 0; i < ns; ++i) { tmp[i] = resize(c, *srcs[i], H, W); a[i] = &tmp[i]; }
+    conv_into(c, L, a, ns, out.p, 0, out.ld, o);
+    return out;
+  }
+  if (!c.live()) return out;
+  pf_gemm_desc d;
+  memset(&d, 0, sizeof(d));
+  d.num_src = ns; d.a_mode = 1;
+  for (int i = 0; i < ns; ++i) {
+    d.a_ptr[i] = srcs[i]->p; d.a_c[i] = pad_to(srcs[i]->C, 8); d.a_ld[i] = srcs[i]->ld;
+    if (srcs[i]->H != H || srcs[i]->W != W) { d.rs_h[i] = srcs[i]->H; d.rs_w[i] = srcs[i]->W; }
+  }
+  d.NB = srcs[0]->B; d.H = H; d.W = W;
+  gemm_desc_common(d, L, o, out.p, 0, out.ld);
+  c.chk(pf_gemm(&d, c.stream));
+  return out;
+}
+
 static Map conv(Ctx& c, const pf_layer& L, const Map* const* srcs, int ns, const GemmOpt& o = GemmOpt()) {
   Map out = c.map(srcs[0]->B, srcs[0]->H, srcs[0]->W, L.N);
   conv_into(c, L, srcs, ns, out.p, 0, out.ld, o);
@@ -403,19 +431,19 @@ static void fusion_run(Ctx& c, const pf_fusion& Wf, const float* crops, const fl
   for (int i = 0; i < 6; ++i) {
     const Map gm = from_pf(g2l_maps[i]);
     const int h = gm.H, w = gm.W;
-    Map e = resize(c, enc[i], h, w);
+    // F.interpolate(enc / previous level / guide, size=(h, w), bilinear, align_corners=True) feeding the 3x3 convs
+    // (guided_fusion_model.py:98-99,191-203)
+    Map e = enc[i];
     if (i > 0) {
-      Map up_prev = resize(c, prev, h, w);
-      Map up_guide = resize(c, guide[i - 1], h, w);
-      const Map* a[3] = {&e, &up_prev, &up_guide};
-      e = conv(c, Wf.up[i - 1][0], a, 3, gr);
+      const Map* a[3] = {&enc[i], &prev, &guide[i - 1]};
+      e = conv_resampled(c, Wf.up[i - 1][0], a, 3, h, w, gr);
       e = conv1(c, Wf.up[i - 1][1], e, gr);
     }
     Map cr = c.map(T, h, w, gm.C);
     if (c.live())
       c.chk(pf_roi_crop_zoom(gm.p, 0, h, w, pad_to(gm.C, 8), gm.ld, boxes, T, static_cast<float>(h) / H, cr.p, cr.ld, 0, c.stream));
     const Map* a2[2] = {&e, &cr};
-    Map y = conv(c, Wf.cv[i][0], a2, 2, gr);
+    Map y = conv_resampled(c, Wf.cv[i][0], a2, 2, h, w, gr);
     prev = conv1(c, Wf.cv[i][1], y, gr);
     outs[i] = prev;
     char nm[16];

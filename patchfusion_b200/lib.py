@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, os.environ.get('PF_B200_LIBNAME', 'libpf_b200.so'))
 
 ACT_NONE, ACT_RELU, ACT_GELU, ACT_SOFTPLUS = 0, 1, 2, 3
-OPT_TMA_EPILOGUE, OPT_HALO_MULTICAST, OPT_GEMM_MULTICAST = 0, 1, 2
+OPT_TMA_EPILOGUE, OPT_HALO_MULTICAST, OPT_GEMM_MULTICAST, OPT_FUSED_RESAMPLE = 0, 1, 2, 3
 
 
 class PFError(RuntimeError):
@@ -38,6 +38,7 @@ class GemmDesc(C.Structure):
         ('vt_dim', C.c_int32),
         ('w2', C.c_void_p), ('b2', C.c_void_p), ('n2', C.c_int32), ('act2', C.c_int32), ('skip_main', C.c_int32),
         ('out3', C.c_void_p), ('out3_ld', C.c_int32),
+        ('rs_h', C.c_int32 * 3), ('rs_w', C.c_int32 * 3),
     ]
 
 

@@ -76,10 +76,11 @@ def pack_weight_convT(weight, bias, k):
 
 def gemm(pw, srcs, out, *, image=None, ps_image=None, M=None, act=ACT_NONE, res1=None, res2=None, gamma=None, out_col0=0, out2=None,
          vt=None, vt_col0=0, vt_seq=0, vt_seq_pad=0, src_c=None, block_n=0, tail=None, tail_out=None,
-         skip_main=False, tile=None):
+         skip_main=False, tile=None, resample=None):
     """srcs: list of bf16 tensors.  image=(NB,H,W) selects NHWC/conv addressing (srcs are [NB,H,W,ld]);
     otherwise srcs are [M, ld] matrices.  `out` may be bf16 or fp32; with `gamma` it is the fp32 residual stream
-    updated in place (x += gamma * (acc + bias))."""
+    updated in place (x += gamma * (acc + bias)).  resample[i] = True: source i is a [NB, h, w, ld] map of another size
+    that the 3x3 conv reads through a fused bilinear (align_corners=True) resample to (H, W)."""
     d = GemmDesc()
     d.num_src = len(srcs)
     d.taps = pw.taps
@@ -91,6 +92,8 @@ def gemm(pw, srcs, out, *, image=None, ps_image=None, M=None, act=ACT_NONE, res1
         d.a_c[i] = pad_to(cs[i], 8)
         d.a_ld[i] = s.shape[-1]
         assert d.a_c[i] <= s.shape[-1]
+        if resample is not None and resample[i]:
+            d.rs_h[i], d.rs_w[i] = s.shape[1], s.shape[2]
     if image is not None:
         d.a_mode = 1
         d.NB, d.H, d.W = image

@@ -149,6 +149,31 @@ def test_conv3x3_halo_without_weight_multicast(cuda, NB, H, W, cs, N, act):
         lib.call('pf_set_option', lib.OPT_HALO_MULTICAST, 1)
 
 
+@pytest.mark.parametrize('NB,H,W,srcs,N', [
+    (2, 28, 37, [(14, 19, 64)], 64),                          # x2 up-sample of one source
+    (3, 56, 74, [(56, 74, 32), (28, 37, 128), (28, 37, 72)], 96),   # plain + two resampled sources (U-Net `up` conv)
+    (2, 40, 52, [(35, 46, 64), (40, 52, 24)], 32),            # non-integer ratio; second source read directly
+    (7, 48, 72, [(24, 36, 136)], 544),                        # >= 148 tiles: with the weight-multicast pairs
+])
+def test_conv3x3_fused_bilinear_resample(cuda, NB, H, W, srcs, N):
+    """pf_gemm_desc.rs_h / rs_w: the conv reads its sources through F.interpolate(bilinear, align_corners=True); the
+    resampled map is produced in the operand stage of the halo kernel and rounded to bf16 like a materialised one"""
+    ops = _ops()
+    g = torch.Generator(device='cuda').manual_seed(H * W + N)
+    cs = [c for _, _, c in srcs]
+    xs = [torch.randn(NB, c, h, w, device=cuda, generator=g) for h, w, c in srcs]
+    w_ = torch.randn(N, sum(cs), 3, 3, device=cuda, generator=g) / (9 * sum(cs)) ** 0.5
+    b = torch.randn(N, device=cuda, generator=g)
+    pw = ops.pack_weight(w_, b, src_c=cs)
+    out = torch.zeros(NB, H, W, ops.pad_to(N, 8), dtype=torch.bfloat16, device=cuda)
+    ops.gemm(pw, [to_nhwc(x) for x in xs], out, image=(NB, H, W), act=ops.ACT_RELU,
+             resample=[(h, w_in) != (H, W) for h, w_in, _ in srcs])
+    up = [rb(x) if tuple(x.shape[-2:]) == (H, W) else rb(F.interpolate(rb(x), size=(H, W), mode='bilinear', align_corners=True))
+          for x in xs]
+    ref = F.relu(F.conv2d(torch.cat(up, 1), rb(w_), b, padding=1))
+    check('conv3x3 fused resample %s -> %d @%dx%d' % (srcs, N, H, W), from_nhwc(out, N), ref, 1e-2)
+
+
 def test_conv3x3_residuals_and_relu_copy(cuda):
     ops = _ops()
     g = torch.Generator(device='cuda').manual_seed(5)
