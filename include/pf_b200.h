@@ -38,18 +38,21 @@ long long pf_launch_count(void);
  * record's kernel name, shape label, algorithmic flops (0 for HBM kernels) and milliseconds. */
 /* Tuning switches (defaults in parentheses; each is also read once from the environment variable of the same name):
  *   PF_OPT_TMA_EPILOGUE (1)   pf_gemm_kernel epilogue through shared memory + bulk tensor stores / reduce-add
- *   PF_OPT_HALO_MULTICAST (1) pf_conv3_halo_kernel in clusters of 2 CTAs sharing the weight tiles by TMA multicast
+ *   PF_OPT_HALO_MULTICAST (1) pf_conv3_halo_kernel in clusters of 2 (value 1) or 4 (value 2) CTAs sharing the weight
+ *                             tiles by TMA multicast
  *   PF_OPT_GEMM_MULTICAST (1) the same for the linear layers of pf_gemm_kernel
  *   PF_OPT_FUSED_RESAMPLE (0) pf_fusion_forward: bilinear resamples feeding the U-Net's 3x3 convs are produced in the
  *                             conv's operand stage (pf_gemm_desc.rs_h / rs_w) instead of being materialised.  Correct
  *                             and parity-tested, but measured SLOWER on B200 (step 215 -> 317 ms): the blend costs ~3.7k
  *                             warp-instructions per 64-channel halo chunk (bf16 <-> fp32 conversion + FFMA2) against
  *                             3.4-4.6k clk of MMA per chunk, and only two warps of the CTA are free to produce it.
+ *   PF_OPT_PDL (0)            programmatic dependent launch for the persistent kernels (measured neutral)
  * Changing one invalidates nothing inside the library; callers holding CUDA graphs must re-capture. */
 #define PF_OPT_TMA_EPILOGUE 0
 #define PF_OPT_HALO_MULTICAST 1
 #define PF_OPT_GEMM_MULTICAST 2
 #define PF_OPT_FUSED_RESAMPLE 3
+#define PF_OPT_PDL 4
 int pf_set_option(int32_t option, int32_t value);
 int pf_profile_start(void* stream);
 int pf_profile_stop(void);

@@ -55,23 +55,24 @@ void count_launch(const char* name) {
   }
 }
 // tuning switches: -1 = not read yet (first use reads the environment variable of the same name)
-static std::atomic<int> g_opt[4] = {{-1}, {-1}, {-1}, {-1}};
+static std::atomic<int> g_opt[5] = {{-1}, {-1}, {-1}, {-1}, {-1}};
 int option(int which) {
-  static const char* names[4] = {"PF_OPT_TMA_EPILOGUE", "PF_OPT_HALO_MULTICAST", "PF_OPT_GEMM_MULTICAST", "PF_OPT_FUSED_RESAMPLE"};
-  static const int defaults[4] = {1, 1, 1, 0};
-  if (which < 0 || which > 3) return 0;
+  static const char* names[5] = {"PF_OPT_TMA_EPILOGUE", "PF_OPT_HALO_MULTICAST", "PF_OPT_GEMM_MULTICAST", "PF_OPT_FUSED_RESAMPLE", "PF_OPT_PDL"};
+  static const int defaults[5] = {1, 1, 1, 0, 0};
+  if (which < 0 || which > 4) return 0;
   int v = g_opt[which].load(std::memory_order_relaxed);
   if (v < 0) {
     const char* e = getenv(names[which]);
-    v = e ? (e[0] != '0') : defaults[which];
+    if (!e && which == PF_OPT_PDL) e = getenv("PF_B200_PDL");
+    v = e ? atoi(e) : defaults[which];
     g_opt[which].store(v, std::memory_order_relaxed);
   }
   return v;
 }
 bool pdl_enabled() {
-  // opt-in (PF_B200_PDL=1): measured neutral inside CUDA graphs on B200, so the default stays the plain launch
-  static const bool on = getenv("PF_B200_PDL") != nullptr && getenv("PF_B200_PDL")[0] == '1';
-  return on;
+  // opt-in (PF_OPT_PDL / legacy PF_B200_PDL=1): measured neutral inside CUDA graphs on B200 (every tensor-core kernel is a
+  // 1-CTA/SM persistent kernel, so a dependent cannot become resident before its predecessor's CTAs retire)
+  return option(PF_OPT_PDL) != 0;
 }
 int check_launch(const char* what) {
   cudaError_t e = cudaGetLastError();
@@ -239,8 +240,8 @@ int pf_version(void) { return 100; }
 long long pf_launch_count(void) { return g_launches.load(); }
 
 int pf_set_option(int32_t which, int32_t value) {
-  if (which < 0 || which > 3) return set_error("pf_set_option: unknown option %d", which);
-  g_opt[which].store(value ? 1 : 0, std::memory_order_relaxed);
+  if (which < 0 || which > 4) return set_error("pf_set_option: unknown option %d", which);
+  g_opt[which].store(value < 0 ? 0 : value, std::memory_order_relaxed);
   return 0;
 }
 
@@ -433,11 +434,16 @@ int pf_gemm(pf_gemm_desc* u, void* stream) {
   if (d.vt && (d.vt_col0 % bn) != 0) return set_error("pf_gemm: vt_col0 must be a multiple of block_n");
   // Linear layers with several m-tiles per n-tile are L2 -> SM bandwidth bound: pairs of CTAs share the weight tile by
   // TMA multicast (PF_OPT_GEMM_MULTICAST / PF_OPT_HALO_MULTICAST).  Needs an even split of the n-tile into 1024-B aligned halves.
-  const bool mc = bn % 16 == 0 && d.m_tiles >= 4 && static_cast<long long>(d.m_tiles) * d.n_tiles >= 148 &&
-                  (halo ? option(PF_OPT_HALO_MULTICAST) != 0
-                        : (option(PF_OPT_GEMM_MULTICAST) != 0 && u->a_mode == 0 && d.ps == 1));
+  // PF_OPT_HALO_MULTICAST: 0 off, 1 clusters of 2, 2 clusters of 4
+  int cl = 1;
+  if (d.m_tiles >= 4 && static_cast<long long>(d.m_tiles) * d.n_tiles >= 148) {
+    if (halo) cl = option(PF_OPT_HALO_MULTICAST) >= 2 ? 4 : (option(PF_OPT_HALO_MULTICAST) == 1 ? 2 : 1);
+    else if (option(PF_OPT_GEMM_MULTICAST) != 0 && u->a_mode == 0 && d.ps == 1 && bn % 16 == 0) cl = 2;
+  }
+  d.halo_cl = halo ? cl : 1;
+  const bool mc = cl > 1;
   CUtensorMap tmBh;
-  if (mc && tmap_2d_bf16(&tmBh, u->w_ptr, u->Ktot, n_pad, u->Ktot, 64, bn / 2)) return 1;
+  if (mc && tmap_2d_bf16(&tmBh, u->w_ptr, u->Ktot, n_pad, u->Ktot, 64, bn / cl)) return 1;
   // Epilogue through shared memory + TMA (pf_gemm_kernel only): plain bf16 outputs in 64-column groups, fp32 outputs
   // and the fp32 residual stream (x += gamma * v) in 32-column chunks.  PF_OPT_TMA_EPILOGUE = 0 keeps the direct stores.
   const bool no_tma_epi = option(PF_OPT_TMA_EPILOGUE) == 0;

@@ -152,19 +152,21 @@ __device__ __forceinline__ void epilogue_chunk(const GemmDesc& d, float (&f)[W],
     for (int i = 0; i < TAILN; ++i) {
       if (i < d.n2) {
         const float* wp = d.w2 + static_cast<long long>(i) * d.n_logical + lcol;
-        float a = 0.f;
+        // four independent partial sums: a single accumulator is a 32-deep FFMA dependency chain, and with two warps
+        // per scheduler the fused-tail layers ran at IPC 0.36 (ncu r02b: latency-bound, no pipe above 16 %)
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
         if (FULL) {
 #pragma unroll
           for (int j = 0; j < W / 4; ++j) {
             float4 w4 = __ldg(reinterpret_cast<const float4*>(wp) + j);
-            a = fmaf(w4.x, f[4 * j], a); a = fmaf(w4.y, f[4 * j + 1], a);
-            a = fmaf(w4.z, f[4 * j + 2], a); a = fmaf(w4.w, f[4 * j + 3], a);
+            a0 = fmaf(w4.x, f[4 * j], a0); a1 = fmaf(w4.y, f[4 * j + 1], a1);
+            a2 = fmaf(w4.z, f[4 * j + 2], a2); a3 = fmaf(w4.w, f[4 * j + 3], a3);
           }
         } else {
 #pragma unroll
-          for (int j = 0; j < W; ++j) if (j < nvalid) a = fmaf(__ldg(wp + j), f[j], a);
+          for (int j = 0; j < W; ++j) if (j < nvalid) a0 = fmaf(__ldg(wp + j), f[j], a0);
         }
-        y2[i] += a;
+        y2[i] += (a0 + a1) + (a2 + a3);
       }
     }
     if (d.skip_main) return;
@@ -475,19 +477,20 @@ __device__ __forceinline__ void epilogue_tile_tma_f32(const GemmDesc& d, EpiTma&
 // where pair p = (m-tile pair p / n_tiles, n-tile p % n_tiles) and the CTA of cluster rank r owns m-tile 2 * mp + r
 // (an odd last m-tile pairs with an all-out-of-range one: TMA zero-fills it, the epilogue drops its rows).
 struct TileIter {
-  int first, step, count, rank, n_tiles;
-  bool mc;
+  int first, step, count, rank, n_tiles, cl;
   __device__ __forceinline__ int tile(int i) const {
-    if (!mc) return i;
+    if (cl == 1) return i;
     const int nt = i % n_tiles, mp = i / n_tiles;
-    return (2 * mp + rank) * n_tiles + nt;
+    return (cl * mp + rank) * n_tiles + nt;
   }
 };
-__device__ __forceinline__ TileIter make_iter(const GemmDesc& d, int total_tiles, bool mc) {
+// cl = CTAs per cluster sharing the weight tiles (1 = plain schedule): cluster g takes work items g, g + clusters, ...
+// where item p = (m-tile group p / n_tiles, n-tile p % n_tiles) and the CTA of cluster rank r owns m-tile cl * group + r.
+__device__ __forceinline__ TileIter make_iter(const GemmDesc& d, int total_tiles, int cl) {
   TileIter it;
-  it.mc = mc; it.n_tiles = d.n_tiles;
-  if (!mc) { it.first = blockIdx.x; it.step = gridDim.x; it.count = total_tiles; it.rank = 0; }
-  else { it.first = blockIdx.x >> 1; it.step = gridDim.x >> 1; it.count = ((d.m_tiles + 1) >> 1) * d.n_tiles; it.rank = cluster_ctarank(); }
+  it.cl = cl; it.n_tiles = d.n_tiles;
+  if (cl == 1) { it.first = blockIdx.x; it.step = gridDim.x; it.count = total_tiles; it.rank = 0; }
+  else { it.first = blockIdx.x / cl; it.step = gridDim.x / cl; it.count = ((d.m_tiles + cl - 1) / cl) * d.n_tiles; it.rank = cluster_ctarank(); }
   return it;
 }
 
@@ -625,7 +628,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) pf_gemm_kernel(const __grid_c
   if (MC) cluster_sync_all();       // the peer's barriers exist before anything is multicast into its shared memory
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const TileIter it = make_iter(d, P.total_tiles, MC);
+  const TileIter it = make_iter(d, P.total_tiles, MC ? 2 : 1);
   pdl_wait();                       // predecessor's results are visible from here on
 
   if (warp == kTmaWarp) {
@@ -756,9 +759,9 @@ constexpr int kHaloSlots = 3;
 // literal at every call site, so all A offsets fold to immediates.
 // full 64-channel chunks take the lean fully unrolled path; only a source's zero-padded last chunk takes the counted one
 #define PF_ISSUE(KC, ...) do { if (nk == kBlockK / 16) issue_taps<KC, true>(__VA_ARGS__); else issue_taps<KC, false>(__VA_ARGS__); } while (0)
-template <bool MC>
+template <int CL>
 __device__ __forceinline__ void halo_release_b(uint64_t* bar) {
-  if (MC) umma_commit_mc(bar, static_cast<uint16_t>(3));    // the weight stage is free in both CTAs of the pair
+  if (CL > 1) umma_commit_mc(bar, static_cast<uint16_t>((1u << CL) - 1));   // the weight stage is free in every CTA of the cluster
   else umma_commit(bar);
 }
 template <int KC, bool FULLK>
@@ -838,12 +841,14 @@ __device__ __forceinline__ void halo_fill_bilinear(uint32_t slot, const GemmDesc
   }
 }
 
-// MC = true: clusters of 2 CTAs take two m-tiles (pixel tiles) of the SAME n-tile; each CTA fetches half of the rows of
-// every weight tile and multicasts it into both CTAs.  The weights are ~90 % of this kernel's L2 -> SM traffic (one
+// CL > 1: clusters of CL (2 or 4) CTAs take CL m-tiles (pixel tiles) of the SAME n-tile; each CTA fetches 1/CL of the rows
+// of every weight tile and multicasts it into all of them.  The weights are ~90 % of this kernel's L2 -> SM traffic (one
 // 23 KB halo against nine 16-32 KB tap tiles per 64-channel chunk) and that traffic sits at the fabric's ceiling
 // (~46 B/clk/SM measured on the linear layers), so halving it is what the N = 32 layers and the partial chunks need.
-template <bool MC>
+template <int CL>
 __global__ void __launch_bounds__(kGemmThreads, 1) pf_conv3_halo_kernel(const __grid_constant__ GemmKernelParams P) {
+  constexpr bool MC = CL > 1;
+  constexpr uint16_t kMask = static_cast<uint16_t>((1u << CL) - 1);
   extern __shared__ uint8_t smem_raw[];
   const GemmDesc& d = P.d;
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -870,17 +875,17 @@ __global__ void __launch_bounds__(kGemmThreads, 1) pf_conv3_halo_kernel(const __
     prefetch_tmap(&P.tmB);
     for (int s = 0; s < kHaloSlots; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
     // a multicast weight stage is refilled only after BOTH CTAs' MMAs released it: two arrivals per phase
-    for (int s = 0; s < stages; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], MC ? 2 : 1); }
+    for (int s = 0; s < stages; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], CL); }
     for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], kEpiWarps * 32); }
     fence_barrier_init();
   }
   if (warp == kMmaWarp) tmem_alloc(tmem_slot, 512);
   tc_fence_before();
   __syncthreads();
-  if (MC) cluster_sync_all();       // the peer's barriers exist before anything is multicast into its shared memory
+  if (MC) cluster_sync_all();       // the peers' barriers exist before anything is multicast into their shared memory
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const TileIter it = make_iter(d, P.total_tiles, MC);
+  const TileIter it = make_iter(d, P.total_tiles, CL);
   pdl_wait();                       // predecessor's results are visible from here on
 
   if (warp == kTmaWarp) {
@@ -906,11 +911,11 @@ __global__ void __launch_bounds__(kGemmThreads, 1) pf_conv3_halo_kernel(const __
             if (elect_one()) {
               mbar_expect_tx(&b_full[bs], b_stage_bytes);
               if (MC) {
-                const int half_rows = d.block_n >> 1;
+                const int part_rows = d.block_n / CL;
                 for (int j = 0; j < kc; ++j)
-                  tma_load_2d_mc(smem_b + bs * b_stage_bytes + j * b_tile_bytes + it.rank * half_rows * 128, &P.tmBh,
-                                 &b_full[bs], (kbase + (tap0 + j) * nch + ch) * kBlockK, c.n0 + it.rank * half_rows,
-                                 static_cast<uint16_t>(3));
+                  tma_load_2d_mc(smem_b + bs * b_stage_bytes + j * b_tile_bytes + it.rank * part_rows * 128, &P.tmBh,
+                                 &b_full[bs], (kbase + (tap0 + j) * nch + ch) * kBlockK, c.n0 + it.rank * part_rows,
+                                 kMask);
               } else {
                 for (int j = 0; j < kc; ++j)
                   tma_load_2d(smem_b + bs * b_stage_bytes + j * b_tile_bytes, &P.tmB, &b_full[bs],
@@ -957,7 +962,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) pf_conv3_halo_kernel(const __
             const uint32_t b_lo = (smem_u32(smem_b + bs * b_stage_bytes) & 0x3FFFF) >> 4;
             if (elect_one()) {
               PF_ISSUE(9, tmem_d, a_hi, a_lo, b_hi, b_lo, b_tile_bytes >> 4, 0, idesc, first, nk);
-              halo_release_b<MC>(&b_empty[bs]);
+              halo_release_b<CL>(&b_empty[bs]);
               umma_commit(&a_empty[as]);                     // halo slot reusable once its 36 MMAs retire
             }
             first = 0;
@@ -972,7 +977,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) pf_conv3_halo_kernel(const __
                 if (g == 0) PF_ISSUE(3, tmem_d, a_hi, a_lo, b_hi, b_lo, b_tile_bytes >> 4, 0, idesc, first, nk);
                 else if (g == 1) PF_ISSUE(3, tmem_d, a_hi, a_lo, b_hi, b_lo, b_tile_bytes >> 4, 3, idesc, first, nk);
                 else PF_ISSUE(3, tmem_d, a_hi, a_lo, b_hi, b_lo, b_tile_bytes >> 4, 6, idesc, first, nk);
-                halo_release_b<MC>(&b_empty[bs]);
+                halo_release_b<CL>(&b_empty[bs]);
                 if (g == 2) umma_commit(&a_empty[as]);
               }
               first = 0;
@@ -986,7 +991,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) pf_conv3_halo_kernel(const __
               const uint32_t b_lo = (smem_u32(smem_b + bs * b_stage_bytes) & 0x3FFFF) >> 4;
               if (elect_one()) {
                 PF_ISSUE(1, tmem_d, a_hi, a_lo, b_hi, b_lo, 0, tap, idesc, first, nk);
-                halo_release_b<MC>(&b_empty[bs]);
+                halo_release_b<CL>(&b_empty[bs]);
                 if (tap == 8) umma_commit(&a_empty[as]);
               }
               first = 0;
@@ -1049,8 +1054,9 @@ int gemm_launch(const GemmDesc& d, const CUtensorMap* tmA, const CUtensorMap& tm
     cudaError_t e = cudaFuncSetAttribute(pf_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(pf_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
     if (e != cudaSuccess) return set_error("cudaFuncSetAttribute(pf_gemm_kernel): %s", cudaGetErrorString(e));
-    e = cudaFuncSetAttribute(pf_conv3_halo_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(pf_conv3_halo_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
+    e = cudaFuncSetAttribute(pf_conv3_halo_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(pf_conv3_halo_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(pf_conv3_halo_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
     if (e != cudaSuccess) return set_error("cudaFuncSetAttribute(pf_conv3_halo_kernel): %s", cudaGetErrorString(e));
     cudaDeviceGetAttribute(&g_sm_counts[dev], cudaDevAttrMultiProcessorCount, dev);
     attr_done[dev] = true;
@@ -1106,21 +1112,34 @@ int gemm_launch(const GemmDesc& d, const CUtensorMap* tmA, const CUtensorMap& tm
     size_t hsmem = 1024 + static_cast<size_t>(kHaloSlots) * kHaloSlot + static_cast<size_t>(hstages) * b_bytes + kTailBytes;
     cudaError_t le;
     if (tmBh != nullptr) {
-      // weight-multicast pairs: clusters of 2 CTAs over (m-tile pair, n-tile) work items
-      const int pairs = ((d.m_tiles + 1) / 2) * d.n_tiles;
-      const int clusters = pairs < g_sm_count / 2 ? pairs : g_sm_count / 2;
+      // weight-multicast clusters of cl CTAs over (m-tile group, n-tile) work items.  Every CTA is persistent, so the grid
+      // must not exceed what is co-resident: ask the driver how many clusters of this shape fit (GPC boundaries).
+      const int cl = d.halo_cl;
+      const int groups = ((d.m_tiles + cl - 1) / cl) * d.n_tiles;
       cudaLaunchConfig_t cfg = {};
-      cfg.gridDim = dim3(2 * clusters); cfg.blockDim = dim3(kGemmThreads); cfg.dynamicSmemBytes = hsmem; cfg.stream = stream;
+      cfg.blockDim = dim3(kGemmThreads); cfg.dynamicSmemBytes = hsmem; cfg.stream = stream;
       cudaLaunchAttribute at[2];
       at[0].id = cudaLaunchAttributeClusterDimension;
-      at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+      at[0].val.clusterDim.x = cl; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
       at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
       at[1].val.programmaticStreamSerializationAllowed = 1;
       cfg.attrs = at;
+      cfg.numAttrs = 1;
+      static int max_clusters[kMaxDevices][5] = {};
+      if (max_clusters[dev][cl] == 0) {
+        cfg.gridDim = dim3(cl * (g_sm_count / cl));
+        int n = 0;
+        cudaError_t qe = cl == 2 ? cudaOccupancyMaxActiveClusters(&n, pf_conv3_halo_kernel<2>, &cfg)
+                                 : cudaOccupancyMaxActiveClusters(&n, pf_conv3_halo_kernel<4>, &cfg);
+        if (qe != cudaSuccess || n < 1) { cudaGetLastError(); n = g_sm_count / cl; }
+        max_clusters[dev][cl] = n < g_sm_count / cl ? n : g_sm_count / cl;
+      }
+      const int clusters = groups < max_clusters[dev][cl] ? groups : max_clusters[dev][cl];
+      cfg.gridDim = dim3(cl * clusters);
       cfg.numAttrs = pdl_enabled() ? 2 : 1;
-      le = cudaLaunchKernelEx(&cfg, pf_conv3_halo_kernel<true>, P);
+      le = cl == 2 ? cudaLaunchKernelEx(&cfg, pf_conv3_halo_kernel<2>, P) : cudaLaunchKernelEx(&cfg, pf_conv3_halo_kernel<4>, P);
     } else {
-      le = launch_pdl(pf_conv3_halo_kernel<false>, dim3(grid), dim3(kGemmThreads), hsmem, stream, P);
+      le = launch_pdl(pf_conv3_halo_kernel<1>, dim3(grid), dim3(kGemmThreads), hsmem, stream, P);
     }
     if (le != cudaSuccess) return set_error("pf_conv3_halo_kernel launch: %s", cudaGetErrorString(le));
   } else if (tmBh != nullptr) {

@@ -12,6 +12,7 @@ namespace pf {
 struct GemmDesc {
   int num_src, a_mode, taps;
   int halo;              // 3x3 conv through the halo-tile kernel (bh=16, bw=8)
+  int halo_cl;           // halo kernel: CTAs per weight-multicast cluster (1, 2 or 4)
   int chunks[3];
   int k_true[3];         // logical channels of each source (profiler flop count)
   int M, NB, H, W, bh, bw, tiles_y, tiles_x, m_tiles;

@@ -138,11 +138,12 @@ def test_conv3x3(cuda, NB, H, W, cs, N, act, tile):
 
 @pytest.mark.parametrize('NB,H,W,cs,N,act', [(5, 50, 70, [96], 64, 'relu'), (7, 48, 72, [40, 64], 544, 'none'),
                                              (7, 48, 72, [136], 32, 'relu')])
-def test_conv3x3_halo_without_weight_multicast(cuda, NB, H, W, cs, N, act):
-    """PF_OPT_HALO_MULTICAST = 0: the same >= 148-tile shapes (which take the cluster-of-2 weight-multicast variant by
-    default, see test_conv3x3) through the plain one-CTA-per-tile schedule"""
+@pytest.mark.parametrize('cluster', [0, 2])
+def test_conv3x3_halo_multicast_variants(cuda, NB, H, W, cs, N, act, cluster):
+    """PF_OPT_HALO_MULTICAST = 0 (one CTA per tile) and 2 (clusters of 4 CTAs): the >= 148-tile shapes that take the
+    cluster-of-2 weight-multicast variant by default (see test_conv3x3)"""
     from patchfusion_b200 import lib
-    lib.call('pf_set_option', lib.OPT_HALO_MULTICAST, 0)
+    lib.call('pf_set_option', lib.OPT_HALO_MULTICAST, cluster)
     try:
         test_conv3x3(cuda, NB, H, W, cs, N, act, None)
     finally:

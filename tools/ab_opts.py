@@ -9,7 +9,7 @@ from bench import build_inputs
 from patchfusion_b200 import lib
 from patchfusion_b200.model import PatchFusion
 
-OPT = dict(tma=lib.OPT_TMA_EPILOGUE, hmc=lib.OPT_HALO_MULTICAST, gmc=lib.OPT_GEMM_MULTICAST, frs=lib.OPT_FUSED_RESAMPLE)
+OPT = dict(tma=lib.OPT_TMA_EPILOGUE, hmc=lib.OPT_HALO_MULTICAST, gmc=lib.OPT_GEMM_MULTICAST, frs=lib.OPT_FUSED_RESAMPLE, pdl=lib.OPT_PDL)
 configs = sys.argv[1:] or ['tma=1,hmc=0', 'tma=1,hmc=1']
 dev = torch.device('cuda:0')
 cfg, sd = build_inputs('vitl')
@@ -19,9 +19,12 @@ model = model.to(dev).eval()
 img = torch.rand(1, 3, 2160, 3840, generator=torch.Generator().manual_seed(100)).to(dev)
 
 
+PN = [9]
+
+
 def step():
     lr = model.make_lr(img)
-    y, _ = model(mode='infer', image_lr=lr, image_hr=img, cai_mode='m2', process_num=9)
+    y, _ = model(mode='infer', image_lr=lr, image_hr=img, cai_mode='m2', process_num=PN[0])
     return y
 
 
@@ -30,7 +33,10 @@ for rnd in range(3):
     for c in configs:
         for kv in c.split(','):
             k, v = kv.split('=')
-            lib.call('pf_set_option', OPT[k], int(v))
+            if k == 'pn':
+                PN[0] = int(v)
+            else:
+                lib.call('pf_set_option', OPT[k], int(v))
         model._graphs = {}
         for _ in range(3):
             step()

@@ -17,6 +17,16 @@ flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)
 
 
 def case(name):
+    if name == 'clbT':      # metric-head CLB: 1x1 [32, 8, 128] -> 80 + GELU with the 80 -> 4 + Softplus layer fused (9 tiles of 392x518)
+        NB, H, W, cs, N = 9, 392, 518, [32, 8, 128], 80
+        srcs = [torch.randn(NB, H, W, c, device=dev).to(torch.bfloat16) for c in cs]
+        w = torch.randn(N, sum(cs), 1, 1, device=dev) / sum(cs) ** 0.5
+        pw = ops.pack_weight(w, torch.randn(N, device=dev), src_c=cs)
+        w2, b2 = torch.randn(4, N, device=dev) / N ** 0.5, torch.randn(4, device=dev)
+        out = torch.empty(NB, H, W, ops.pad_to(N, 8), dtype=torch.bfloat16, device=dev)
+        pt = torch.empty(NB, H, W, 8, dtype=torch.float32, device=dev)
+        return lambda: ops.gemm(pw, srcs, out, image=(NB, H, W), act=ops.ACT_GELU, tail=(w2, b2, ops.ACT_SOFTPLUS),
+                                tail_out=pt, skip_main=True)
     K, N = dict(proj=(1024, 1024), fc2=(4096, 1024), fc1=(1024, 4096), qkv=(1024, 3072))[name]
     w = torch.randn(N, K, device=dev) / K ** 0.5
     pw = ops.pack_weight(w, torch.randn(N, device=dev))
