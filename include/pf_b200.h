@@ -47,12 +47,15 @@ long long pf_launch_count(void);
  *                             warp-instructions per 64-channel halo chunk (bf16 <-> fp32 conversion + FFMA2) against
  *                             3.4-4.6k clk of MMA per chunk, and only two warps of the CTA are free to produce it.
  *   PF_OPT_PDL (0)            programmatic dependent launch for the persistent kernels (measured neutral)
+ *   PF_OPT_RESIZE_SEPARABLE (0) tiled bilinear resample: x blend once per source row, then one y blend per output row
+ *                             (3x fewer ALU instructions; measured neutral - the FFMA2 4-tap form is no longer ALU-bound)
  * Changing one invalidates nothing inside the library; callers holding CUDA graphs must re-capture. */
 #define PF_OPT_TMA_EPILOGUE 0
 #define PF_OPT_HALO_MULTICAST 1
 #define PF_OPT_GEMM_MULTICAST 2
 #define PF_OPT_FUSED_RESAMPLE 3
 #define PF_OPT_PDL 4
+#define PF_OPT_RESIZE_SEPARABLE 5
 int pf_set_option(int32_t option, int32_t value);
 int pf_profile_start(void* stream);
 int pf_profile_stop(void);

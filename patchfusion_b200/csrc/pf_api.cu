@@ -55,11 +55,11 @@ void count_launch(const char* name) {
   }
 }
 // tuning switches: -1 = not read yet (first use reads the environment variable of the same name)
-static std::atomic<int> g_opt[5] = {{-1}, {-1}, {-1}, {-1}, {-1}};
+static std::atomic<int> g_opt[6] = {{-1}, {-1}, {-1}, {-1}, {-1}, {-1}};
 int option(int which) {
-  static const char* names[5] = {"PF_OPT_TMA_EPILOGUE", "PF_OPT_HALO_MULTICAST", "PF_OPT_GEMM_MULTICAST", "PF_OPT_FUSED_RESAMPLE", "PF_OPT_PDL"};
-  static const int defaults[5] = {1, 1, 1, 0, 0};
-  if (which < 0 || which > 4) return 0;
+  static const char* names[6] = {"PF_OPT_TMA_EPILOGUE", "PF_OPT_HALO_MULTICAST", "PF_OPT_GEMM_MULTICAST", "PF_OPT_FUSED_RESAMPLE", "PF_OPT_PDL", "PF_OPT_RESIZE_SEPARABLE"};
+  static const int defaults[6] = {1, 1, 1, 0, 0, 0};
+  if (which < 0 || which > 5) return 0;
   int v = g_opt[which].load(std::memory_order_relaxed);
   if (v < 0) {
     const char* e = getenv(names[which]);
@@ -240,7 +240,7 @@ int pf_version(void) { return 100; }
 long long pf_launch_count(void) { return g_launches.load(); }
 
 int pf_set_option(int32_t which, int32_t value) {
-  if (which < 0 || which > 4) return set_error("pf_set_option: unknown option %d", which);
+  if (which < 0 || which > 5) return set_error("pf_set_option: unknown option %d", which);
   g_opt[which].store(value < 0 ? 0 : value, std::memory_order_relaxed);
   return 0;
 }

@@ -9,7 +9,7 @@ from bench import build_inputs
 from patchfusion_b200 import lib
 from patchfusion_b200.model import PatchFusion
 
-OPT = dict(tma=lib.OPT_TMA_EPILOGUE, hmc=lib.OPT_HALO_MULTICAST, gmc=lib.OPT_GEMM_MULTICAST, frs=lib.OPT_FUSED_RESAMPLE, pdl=lib.OPT_PDL)
+OPT = dict(tma=lib.OPT_TMA_EPILOGUE, hmc=lib.OPT_HALO_MULTICAST, gmc=lib.OPT_GEMM_MULTICAST, frs=lib.OPT_FUSED_RESAMPLE, pdl=lib.OPT_PDL, sep=lib.OPT_RESIZE_SEPARABLE)
 configs = sys.argv[1:] or ['tma=1,hmc=0', 'tma=1,hmc=1']
 dev = torch.device('cuda:0')
 cfg, sd = build_inputs('vitl')
