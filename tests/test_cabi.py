@@ -111,3 +111,22 @@ def test_stage_struct_layouts(tmp_path):
             assert getattr(cls, field).offset == int(v), (cname, field)
         n += 1
     assert n > 100
+
+
+def test_tuning_options_match_header_and_validate():
+    """PF_OPT_* of include/pf_b200.h == lib.OPT_*; pf_set_option is a pure host call: accepts every declared option,
+    rejects unknown ones with a message (no GPU needed)"""
+    from patchfusion_b200 import lib
+    src = open(HDR).read()
+    opts = dict(re.findall(r'#define\s+(PF_OPT_[A-Z_]+)\s+(\d+)', src))
+    assert len(opts) >= 6
+    for name, val in opts.items():
+        assert getattr(lib, name[3:]) == int(val), name
+    h = lib.load()
+    for val in opts.values():
+        assert h.pf_set_option(int(val), 1) == 0
+    assert h.pf_set_option(99, 1) != 0 and b'unknown option' in h.pf_last_error()
+    # restore the documented defaults for the other tests of this process
+    for name, default in (('PF_OPT_TMA_EPILOGUE', 1), ('PF_OPT_HALO_MULTICAST', 1), ('PF_OPT_GEMM_MULTICAST', 1),
+                          ('PF_OPT_FUSED_RESAMPLE', 0), ('PF_OPT_PDL', 0), ('PF_OPT_RESIZE_SEPARABLE', 0)):
+        assert h.pf_set_option(int(opts[name]), default) == 0
