@@ -38,9 +38,22 @@ if what == 'kernels':
     qkv = torch.randn(24 * 24, 3 * 64, device=dev, generator=g).to(bf)
     ow = torch.zeros(24 * 24, 64, dtype=bf, device=dev)
     ops.call('pf_window_attention', qkv, torch.randn(529, 8, device=dev, generator=g), 24, 24, 64, 8, 6, ow, ops.stream_ptr())
+    # round 2b: fp32 residual stream through the bulk reduce-add epilogue, bf16 bulk-store epilogue on an NHWC 1x1 conv,
+    # and a >= 148-tile 3x3 conv (weight-multicast CTA pairs of the halo kernel, odd m-tile count -> one phantom tile)
+    xs = torch.zeros(300, 256, dtype=torch.float32, device=dev)
+    pg = ops.pack_weight(torch.randn(256, 192, device=dev, generator=g) / 14, torch.randn(256, device=dev, generator=g))
+    ops.gemm(pg, [x], xs, gamma=torch.rand(256, device=dev, generator=g))
+    p1 = ops.pack_weight(torch.randn(128, 64, 1, 1, device=dev, generator=g) / 8, torch.randn(128, device=dev, generator=g))
+    o1 = torch.zeros(1, 40, 36, 128, dtype=bf, device=dev)
+    ops.gemm(p1, [xi], o1, image=(1, 40, 36), act=ops.ACT_RELU)
+    xc = torch.randn(7, 48, 72, 40, device=dev, generator=g).to(bf)
+    pcm = ops.pack_weight(torch.randn(64, 40, 3, 3, device=dev, generator=g) / 19, torch.randn(64, device=dev, generator=g))
+    ocm = torch.zeros(7, 48, 72, 64, dtype=bf, device=dev)
+    ops.gemm(pcm, [xc], ocm, image=(7, 48, 72), act=ops.ACT_RELU)
     torch.cuda.synchronize()
     print('kernels ok', float(out.float().abs().mean()), float(om.float().abs().mean()), float(oc.float().abs().mean()),
-          float(oa.float().abs().mean()), float(ow.float().abs().mean()))
+          float(oa.float().abs().mean()), float(ow.float().abs().mean()), float(xs.abs().mean()),
+          float(o1.float().abs().mean()), float(ocm.float().abs().mean()))
 else:
     from patchfusion_b200.configs import depth_anything_patchfusion
     from patchfusion_b200.model import PatchFusion
